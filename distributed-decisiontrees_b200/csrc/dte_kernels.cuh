@@ -1,0 +1,429 @@
+// dte_kernels.cuh — sm_100a tree-walk kernels of the B200 decision-tree-ensemble engine.
+//
+// What they compute (per tuple x, complete trees, one device) is the reference's Core output
+// (rtl/DTEngine/Core.sv:486-542 on top of core/DTPUCluster.sv:188-222 and core/DTPU.sv:579-761):
+//
+//   score(x) = SUM_seq{j<K}  SUM_seq{s<S}  tree8{p<8}( leaf(x, tree t = (s*K + j)*8 + p) )
+//   leaf(x,t): n = 0; D times { right = (x[fi] == missing) ? fi.bit13 : !((int32)x[fi] < (int32)thr); n = 2n+1+right }
+//   tree8(l)  = ((l0+l1)+(l2+l3))+((l4+l5)+(l6+l7)),  every add = add.rn.ftz.f32
+//
+// B200 mapping (nothing here resembles the FPGA pipeline):
+//   * lane = tuple.  A warp owns 32 tuples and walks the SAME tree in all lanes, so the upper tree
+//     levels are shared-memory / L1 broadcasts and the tuple tile can be stored feature-major
+//     (xs[f][column]) which makes every per-lane feature fetch bank-conflict free.
+//   * one lane accumulates all trees of its tuple in the reference's summation order, so scores
+//     are bit-exact with the oracle; ILP comes from walking 4 or 8 trees of a tree8 group at once.
+//   * the ensemble is repacked on load: levels 0..D-3 as 8-byte heap records ("top"), and the two
+//     last comparison levels plus their four leaves as ONE 32-byte sector-aligned record
+//     ("bottom") — the deep, divergent part of a walk costs one L2 sector instead of three.
+//   * TILE_STAGED: a producer warp streams the top parts of the next trees into a shared-memory
+//     ring with cp.async.bulk + mbarrier (TMA bulk copy engine) while the consumer warps walk.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dte {
+
+struct WalkParams {
+    const uint2* top;           // [trees_padded][top_stride] {thr bits, fidx | (8+8*missing_right)<<16}
+    const uint4* bottom;        // [trees_padded][nb][BOT_VEC] see repack in dte_engine.cu
+    const float* tuples;        // [n][F] row-major fp32 (the reference's tuple CLs)
+    float* scores;              // [n]
+    uint8_t* labels;            // [n] or nullptr
+    unsigned long long n;
+    uint32_t F;
+    uint32_t Dtop;              // comparison levels held in `top` (= max(D,2) - 2)
+    uint32_t top_stride;        // records per tree in `top` (= max(1, 2^Dtop))
+    uint32_t nb;                // bottom records per tree (= 2^Dtop)
+    uint32_t groups;            // tree8 groups to walk (= min(S*K, ceil(T/8)))
+    uint32_t K;                 // clusters per tuple: group g accumulates into partial g % K
+    uint32_t missing;           // raw missing-value pattern
+    uint32_t tiles;             // ceil(n / tuples_per_cta)
+    uint32_t nwarps;            // consumer warps per CTA (tuples_per_cta = 32 * nwarps)
+    uint32_t nstages;           // ring depth (TILE_STAGED)
+};
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fadd_ref(float a, float b) {
+    // the reference adder: round-to-nearest-even, no subnormals (FPAdder_2cycles_latency.v:360-386)
+    float r;
+    asm("add.rn.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint2 ldg64_nc(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128_nc(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg128_stream(const void* p) {   // tuples: read once, keep out of L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// bulk async copy global -> shared of this CTA, completion counted on an mbarrier (TMA bulk engine)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// direction of one node step as a byte increment on the 8-byte heap offset: left 8, right 16
+__device__ __forceinline__ uint32_t step_inc(uint32_t x, uint32_t thr, uint32_t meta, uint32_t missing) {
+    uint32_t inc = ((int32_t)x < (int32_t)thr) ? 8u : 16u;   // go right iff !(x < thr), DTPU.sv:655-657
+    if (x == missing) inc = meta >> 16;                       // DTPU.sv:653,659,667
+    return inc;
+}
+
+// select partial `j` out of a register file of 8 (j is warp-uniform)
+__device__ __forceinline__ float acc_get(const float (&a)[8], uint32_t j) {
+    float v = a[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) v = (j == (uint32_t)i) ? a[i] : v;
+    return v;
+}
+__device__ __forceinline__ void acc_set(float (&a)[8], uint32_t j, float v) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (j == (uint32_t)i) ? v : a[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// bottom record: two comparison levels + four leaves.
+//   compact (every feature index < 512), 32 B:  {thr_p, thr_l, thr_r, fpack} {leaf LL, LR, RL, RR}
+//       fpack = fp | fl<<10 | fr<<20, each 10-bit field = fidx | missing_right<<9
+//   wide (any index < 2048), 64 B: {thr_p, thr_l, thr_r, meta_p} {meta_l, meta_r, 0, 0} {leaves} {0}
+//       meta = fidx | missing_right<<16
+// FEAT(f) fetches feature f of this lane's tuple.
+// ---------------------------------------------------------------------------------------------
+template <bool WIDE> struct BotRec {
+    uint4 a, b, c;
+};
+template <bool WIDE> __device__ __forceinline__ void bot_load(BotRec<WIDE>& r, const uint4* rec) {
+    r.a = ldg128_nc(rec);
+    r.b = ldg128_nc(rec + 1);
+    if (WIDE) r.c = ldg128_nc(rec + 2);
+}
+template <bool WIDE, class Feat>
+__device__ __forceinline__ float bot_finish(const BotRec<WIDE>& r, uint32_t missing, Feat feat) {
+    uint32_t fp, fl, fr, mp, ml, mr;
+    uint4 leaves;
+    if (WIDE) {
+        fp = r.a.w & 0xFFFFu; mp = r.a.w >> 16;
+        fl = r.b.x & 0xFFFFu; ml = r.b.x >> 16;
+        fr = r.b.y & 0xFFFFu; mr = r.b.y >> 16;
+        leaves = r.c;
+    } else {
+        uint32_t k = r.a.w;
+        fp = k & 0x1FFu;         mp = (k >> 9) & 1u;
+        fl = (k >> 10) & 0x1FFu; ml = (k >> 19) & 1u;
+        fr = (k >> 20) & 0x1FFu; mr = (k >> 29) & 1u;
+        leaves = r.b;
+    }
+    // all three features are fetched up front (conflict-free in the tile kernels): one dependent
+    // round trip instead of two
+    uint32_t xp = feat(fp), xl = feat(fl), xr = feat(fr);
+    bool r1 = (xp == missing) ? (mp != 0) : !((int32_t)xp < (int32_t)r.a.x);
+    uint32_t thr = r1 ? r.a.z : r.a.y;
+    uint32_t xc = r1 ? xr : xl;
+    uint32_t mc = r1 ? mr : ml;
+    bool r2 = (xc == missing) ? (mc != 0) : !((int32_t)xc < (int32_t)thr);
+    uint32_t lo = r2 ? leaves.y : leaves.x;
+    uint32_t hi = r2 ? leaves.w : leaves.z;
+    return __uint_as_float(r1 ? hi : lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1 — generic: one thread per tuple, nodes AND features from global memory.
+// Any F (up to 2047) and any D; used when the feature-major tile does not fit shared memory and as
+// an independent cross-check of the tile kernels in the tests.
+// ---------------------------------------------------------------------------------------------
+template <bool WIDE>
+__global__ void __launch_bounds__(128) dt_walk_generic(const WalkParams p) {
+    constexpr int BV = WIDE ? 4 : 2;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t* x = reinterpret_cast<const uint32_t*>(p.tuples) + i * p.F;
+    auto feat = [&](uint32_t f) { return __ldg(x + f); };
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    for (uint32_t g = 0; g < p.groups; ++g) {
+        float l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = 0.0f;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t t = g * 8 + q;
+            const char* tp = reinterpret_cast<const char*>(p.top + (size_t)t * p.top_stride);
+            uint32_t o = 0;
+            for (uint32_t lvl = 0; lvl < p.Dtop; ++lvl) {
+                uint2 nd = ldg64_nc(tp + o);
+                uint32_t xv = feat(nd.y & 0xFFFFu);
+                o = 2 * o + step_inc(xv, nd.x, nd.y, p.missing);
+            }
+            const uint32_t j = (o >> 3) - (p.nb - 1);
+            BotRec<WIDE> br;
+            bot_load<WIDE>(br, p.bottom + ((size_t)t * p.nb + j) * BV);
+            float leaf = bot_finish<WIDE>(br, p.missing, feat);
+            // static register index for l[q]
+#pragma unroll
+            for (int k = 0; k < 8; ++k) l[k] = (k == q) ? leaf : l[k];
+        }
+        float r = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
+                           fadd_ref(fadd_ref(l[4], l[5]), fadd_ref(l[6], l[7])));
+        const uint32_t j = g % p.K;
+        acc_set(acc, j, fadd_ref(r, acc_get(acc, j)));    // acc = r + acc, FPAggregator.v:79-131
+    }
+    float tot = 0.0f;
+    for (uint32_t j = 0; j < p.K; ++j) tot = fadd_ref(acc_get(acc, j), tot);   // Core.sv:486-542
+    p.scores[i] = tot;
+    if (p.labels) p.labels[i] = tot > 0.0f ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2/3 — tile kernels.  Persistent CTAs (one per SM); CTA = nwarps consumer warps
+// (+ 1 producer warp when STAGED).  Shared memory:
+//   [0,128)                       mbarriers: full[nstages], empty[nstages]
+//   [128, 128 + ring)             STAGED: nstages x ILP tree tops (ILP * top_stride * 8 B each)
+//   [.., + F * M * 4)             xs[f][M] feature-major tuple tile, M = 32 * nwarps columns
+// Warp w owns columns 32w..32w+31 exclusively, so tile reloads need no CTA-wide barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kBarBytes = 128;
+
+template <int ILP, bool STAGED, bool WIDE>
+__global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
+    constexpr int BV = WIDE ? 4 : 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t M = 32u * p.nwarps;
+    const uint32_t tree_bytes = p.top_stride * 8u;
+    const uint32_t stage_bytes = (uint32_t)ILP * tree_bytes;
+    const uint32_t ring_bytes = STAGED ? p.nstages * stage_bytes : 0u;
+    const uint32_t xs_base = sbase + kBarBytes + ring_bytes;
+    const uint32_t row_bytes = M * 4u;
+    const uint32_t steps = p.groups * (8 / ILP);       // ILP trees per step
+    const uint32_t my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (STAGED) {
+        if (threadIdx.x == 0) {
+            for (uint32_t s = 0; s < p.nstages; ++s) {
+                mbar_init(sbase + 8 * s, 1);                        // full: producer's arrive + tx bytes
+                mbar_init(sbase + 8 * (p.nstages + s), p.nwarps);   // empty: one arrive per consumer warp
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (warp == p.nwarps) {
+            // ---------------- producer: stream tree tops through the ring ----------------
+            if (lane == 0) {
+                const uint64_t total = (uint64_t)my_tiles * steps;
+                const char* src0 = reinterpret_cast<const char*>(p.top);
+                uint32_t slot = 0, par = 1;                          // fresh barrier: parity-1 wait passes
+                uint32_t q = 0;
+                for (uint64_t it = 0; it < total; ++it) {
+                    mbar_wait(sbase + 8 * (p.nstages + slot), par);
+                    const uint32_t full = sbase + 8 * slot;
+                    mbar_arrive_expect_tx(full, stage_bytes);
+                    const uint32_t dst = sbase + kBarBytes + slot * stage_bytes;
+                    const char* src = src0 + (size_t)q * stage_bytes;
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
+                    if (++q == steps) q = 0;
+                    if (++slot == p.nstages) { slot = 0; par ^= 1; }
+                }
+            }
+            return;
+        }
+    }
+
+    // ---------------- consumers ----------------
+    const uint32_t col = warp * 32u + lane;
+    const uint32_t xcol = xs_base + col * 4u;
+    auto feat = [&](uint32_t f) { return lds32(xcol + f * row_bytes); };
+    uint32_t slot = 0, par = 0;
+
+    for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        // ---- load this warp's 32 tuples, transposing row-major global -> feature-major shared ----
+        __syncwarp();
+        {
+            const unsigned long long m = (unsigned long long)tile * M + col;
+            const bool live = m < p.n;
+            const uint4* row = reinterpret_cast<const uint4*>(p.tuples + (live ? m : 0ull) * p.F);
+            const uint32_t nvec = p.F >> 2;
+            uint32_t v = 0;
+            for (; v + 4 <= nvec; v += 4) {
+                uint4 d0 = ldg128_stream(row + v), d1 = ldg128_stream(row + v + 1);
+                uint4 d2 = ldg128_stream(row + v + 2), d3 = ldg128_stream(row + v + 3);
+                if (!live) { d0 = d1 = d2 = d3 = make_uint4(0, 0, 0, 0); }
+                uint32_t a = xcol + (4 * v) * row_bytes;
+                sts32(a, d0.x); sts32(a + row_bytes, d0.y); sts32(a + 2 * row_bytes, d0.z); sts32(a + 3 * row_bytes, d0.w);
+                a += 4 * row_bytes;
+                sts32(a, d1.x); sts32(a + row_bytes, d1.y); sts32(a + 2 * row_bytes, d1.z); sts32(a + 3 * row_bytes, d1.w);
+                a += 4 * row_bytes;
+                sts32(a, d2.x); sts32(a + row_bytes, d2.y); sts32(a + 2 * row_bytes, d2.z); sts32(a + 3 * row_bytes, d2.w);
+                a += 4 * row_bytes;
+                sts32(a, d3.x); sts32(a + row_bytes, d3.y); sts32(a + 2 * row_bytes, d3.z); sts32(a + 3 * row_bytes, d3.w);
+            }
+            for (; v < nvec; ++v) {
+                uint4 d0 = ldg128_stream(row + v);
+                if (!live) d0 = make_uint4(0, 0, 0, 0);
+                uint32_t a = xcol + (4 * v) * row_bytes;
+                sts32(a, d0.x); sts32(a + row_bytes, d0.y); sts32(a + 2 * row_bytes, d0.z); sts32(a + 3 * row_bytes, d0.w);
+            }
+        }
+        __syncwarp();
+
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+        float half0 = 0.0f;
+
+        for (uint32_t q = 0; q < steps; ++q) {
+            const uint32_t t0 = q * ILP;
+            uint32_t o[ILP];
+#pragma unroll
+            for (int c = 0; c < ILP; ++c) o[c] = 0;
+
+            if (STAGED) {
+                mbar_wait(sbase + 8 * slot, par);
+                const uint32_t tb = sbase + kBarBytes + slot * stage_bytes;
+                for (uint32_t lvl = 0; lvl < p.Dtop; ++lvl) {
+                    uint2 nd[ILP];
+                    uint32_t xv[ILP];
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) nd[c] = lds64(tb + c * tree_bytes + o[c]);
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) xv[c] = feat(nd[c].y & 0xFFFFu);
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) o[c] = 2 * o[c] + step_inc(xv[c], nd[c].x, nd[c].y, p.missing);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sbase + 8 * (p.nstages + slot));
+                if (++slot == p.nstages) { slot = 0; par ^= 1; }
+            } else {
+                const char* tp = reinterpret_cast<const char*>(p.top + (size_t)t0 * p.top_stride);
+                for (uint32_t lvl = 0; lvl < p.Dtop; ++lvl) {
+                    uint2 nd[ILP];
+                    uint32_t xv[ILP];
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) nd[c] = ldg64_nc(tp + (size_t)c * tree_bytes + o[c]);
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) xv[c] = feat(nd[c].y & 0xFFFFu);
+#pragma unroll
+                    for (int c = 0; c < ILP; ++c) o[c] = 2 * o[c] + step_inc(xv[c], nd[c].x, nd[c].y, p.missing);
+                }
+            }
+
+            // ---- bottom: last two comparison levels + leaves, one 32 B (64 B) record per walk ----
+            BotRec<WIDE> br[ILP];
+#pragma unroll
+            for (int c = 0; c < ILP; ++c) {
+                const uint32_t j = (o[c] >> 3) - (p.nb - 1);
+                bot_load<WIDE>(br[c], p.bottom + ((size_t)(t0 + c) * p.nb + j) * BV);
+            }
+            float l[ILP];
+#pragma unroll
+            for (int c = 0; c < ILP; ++c) l[c] = bot_finish<WIDE>(br[c], p.missing, feat);
+
+            // ---- tree8 reduce + accumulation in the reference's order ----
+            float r;
+            bool group_done;
+            if constexpr (ILP == 8) {
+                r = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
+                             fadd_ref(fadd_ref(l[4], l[5]), fadd_ref(l[6], l[7])));
+                group_done = true;
+            } else {
+                float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
+                group_done = (q & 1u) != 0;
+                r = fadd_ref(half0, h);
+                half0 = h;
+            }
+            if (group_done) {
+                const uint32_t j = (q / (8 / ILP)) % p.K;
+                acc_set(acc, j, fadd_ref(r, acc_get(acc, j)));
+            }
+        }
+
+        float tot = 0.0f;
+        for (uint32_t j = 0; j < p.K; ++j) tot = fadd_ref(acc_get(acc, j), tot);
+        const unsigned long long m = (unsigned long long)tile * M + col;
+        if (m < p.n) {
+            p.scores[m] = tot;
+            if (p.labels) p.labels[m] = tot > 0.0f ? 1 : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers: labels, one ring-add hop, synthetic tuples
+// ---------------------------------------------------------------------------------------------
+__global__ void labels_kernel(const float* __restrict__ s, uint8_t* __restrict__ l, unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) l[i] = s[i] > 0.0f ? 1 : 0;
+}
+__global__ void ring_add_kernel(const float* a, const float* b, float* out, unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fadd_ref(a[i], b[i]);       // ResultsCombiner.sv:292-311, one hop
+}
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void synth_tuples_kernel(uint32_t* out, unsigned long long first_elem, unsigned long long n_elem,
+                                    unsigned long long seed, uint32_t missing_ppm, uint32_t missing_value) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n_elem; i += stride) {
+        unsigned long long z = splitmix64(seed, first_elem + i);
+        float v = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);      // 24 bits -> [0,1), exact
+        uint32_t bits = __float_as_uint(v);
+        if ((uint32_t)(z & 0xFFFFFFFFull) % 1000000u < missing_ppm) bits = missing_value;
+        out[i] = bits;
+    }
+}
+
+}  // namespace dte

@@ -1,0 +1,147 @@
+/*
+ * dte.h — C ABI of the B200 decision-tree-ensemble inference engine (libdte.so).
+ *
+ * Drop-in boundary for ONE hot path of fpgasystems/Distributed-DecisionTrees: the `Core` tree walk
+ * plus the `ResultsCombiner` aggregation.  The reference exposes that path as a HARDWARE interface
+ * (soft-register bus + 128-bit PCIe DMA lines); there is no host driver or C header in the
+ * reference repository.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root).  A host program written against the Catapult shell
+ * replays its register writes and DMA buffers through these calls unchanged.
+ *
+ * Conventions: plain C types only; every call returns 0 (DTE_OK) or a negative dte_status; the
+ * caller owns all buffers; one handle = one in-order engine (calls on one handle are serialised by
+ * the caller, distinct handles are independent); nothing throws across the boundary; there is no
+ * CPU fallback — without a CUDA device dte_create fails with DTE_ERR_CUDA.
+ *
+ * "CL" = one 128-bit line = 4 little-endian 32-bit words = 8 little-endian 16-bit words
+ * (rtl/DTEngine/common/DTEngine_Types.sv:20-27, word order rtl/DTEngine/core/PipelinedMUX.sv:63-65).
+ */
+#ifndef DTE_H
+#define DTE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dte_engine dte_t;
+
+typedef enum {
+    DTE_OK = 0,
+    DTE_ERR_ARG = -1,          /* null pointer, bad size, bad register value */
+    DTE_ERR_STATE = -2,        /* call not legal in the current stream state */
+    DTE_ERR_CONFIG = -3,       /* CSR contents inconsistent (e.g. line counts too small for D) */
+    DTE_ERR_UNSUPPORTED = -4,  /* ensemble uses a feature outside the contract (bit 14, index >= F) */
+    DTE_ERR_CUDA = -5,         /* CUDA runtime error or no device */
+    DTE_ERR_NOMEM = -6
+} dte_status;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* One engine bound to CUDA device `gpu_ordinal`.  Replaces: power-on reset of one FPGA role
+ * (rtl/SimpleRole.sv:29-63).  The loaded ensemble survives any number of `start`s, as the PU
+ * tree memories survive everything but a hardware reset (rtl/DTEngine/core/DTPU.sv:307-319). */
+int dte_create(dte_t** engine, int gpu_ordinal);
+int dte_destroy(dte_t* engine);
+/* Last error text for this handle (never NULL; valid until the next call on the handle). */
+const char* dte_last_error(const dte_t* engine);
+
+/* ---- soft registers ------------------------------------------------------------------------ */
+/* Replaces the SoftRegReq/SoftRegResp bus, addresses >= 200 (rtl/ManagerSoftRegs.sv:63):
+ * writes 200..211 as decoded in rtl/DTEngine/EngineCSR.sv:189-306, reads 220..226 as in
+ * EngineCSR.sv:113-125 (222/223 = progCycles/execCycles, here in nanoseconds of device time),
+ * 121..126 = appStatus counters (rtl/ManagerSoftRegs.sv:122-127); any other read address returns
+ * 0xFFFFFFFFFFFFFFFF like EngineCSR.sv:123. Writing bit 0 of register 200 is `start`. */
+int dte_softreg_write(dte_t* engine, uint32_t addr, uint64_t data);
+int dte_softreg_read(dte_t* engine, uint32_t addr, uint64_t* data);
+
+/* ---- PCIe line streams --------------------------------------------------------------------- */
+/* Replaces the PCIe DMA input stream of slot >= 1 (rtl/PCIeShim.sv:99-100,124-141) in the order
+ * rtl/DTEngine/PCIeReceiver.sv:136-139,205-316 consumes it after `start`:
+ *   all weight CLs of all trees (reg 202[63:32] lines) -> all feature-index CLs (until
+ *   reg 202[31:0]) -> tuple CLs.  With host_node=0 and data_distributed=1 (reg 201) the stream is
+ *   tuple CLs only and the resident ensemble is reused.  May be called with any chunking. */
+int dte_stream_write(dte_t* engine, const void* cl128, size_t n_lines);
+/* Replaces the PCIe DMA output stream written by rtl/DTEngine/ResultsCombiner.sv:132-162,426-454:
+ * result CLs, 4 fp32 scores each, tuple order.  Copies up to max_lines finished lines, never
+ * blocks; *got = lines copied.  A trailing group of fewer than 4 results stays inside the engine
+ * exactly as in the RTL (ResultsCombiner.sv:153-155). */
+int dte_stream_read(dte_t* engine, void* cl128, size_t max_lines, size_t* got);
+/* 1 when as many result lines as reg 207[31:0] asks for have been produced
+ * (process_done, rtl/DTEngine/DTInference.sv:633-663). */
+int dte_process_done(dte_t* engine, int* done);
+
+/* ---- fast paths (same engine, same kernels, no line framing) -------------------------------- */
+/* Program the ensemble from the two tree streams held in host memory, using the geometry already
+ * written to registers 204/205.  Equivalent to `start` + streaming those lines.
+ * first_tree/num_local_trees select the contiguous chunk this device keeps — the chunking
+ * PCIeReceiver does by numcls_local_weights/findexes (PCIeReceiver.sv:241-264); pass 0 / all trees
+ * for a single device or for the data-sharded (replicated) mode. */
+int dte_load_ensemble(dte_t* engine, const void* weight_cls, size_t n_weight_cls,
+                      const void* findex_cls, size_t n_findex_cls,
+                      uint32_t first_tree, uint32_t num_local_trees);
+
+/* Scores (and optionally labels = score > 0.0f, may be NULL) for n tuples that already sit in
+ * device memory as n*tuple_numcls CLs (row-major fp32 [n][F]).  Asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*; NULL = the engine's own stream, then the call synchronises). */
+int dte_infer_device(dte_t* engine, const void* d_tuples, size_t n, float* d_scores,
+                     uint8_t* d_labels, void* cuda_stream);
+
+/* Same from host memory: chunks, overlaps H2D / walk / D2H on the engine's streams, returns when
+ * h_scores (and h_labels if not NULL) are complete.  Pinned host buffers give full PCIe speed. */
+int dte_infer_host(dte_t* engine, const void* h_tuples, size_t n, float* h_scores, uint8_t* h_labels);
+
+/* labels[i] = scores[i] > 0.0f on the device (used after a cross-device reduce). */
+int dte_labels_device(dte_t* engine, const float* d_scores, size_t n, uint8_t* d_labels, void* cuda_stream);
+
+/* lane-wise out[i] = a[i] + b[i] with the engine's adder (add.rn.ftz.f32): one hop of the
+ * ResultsCombiner ring (ResultsCombiner.sv:292-311).  out may alias a or b. */
+int dte_ring_add_device(dte_t* engine, const float* d_a, const float* d_b, float* d_out, size_t n, void* cuda_stream);
+
+/* ---- parameters in the profiler's vocabulary ------------------------------------------------ */
+/* The reference's only C++ parameter surface is profiler/profiler.cpp:31-41 (N_trees, Depth_tree,
+ * Size_tuple_Bytes).  This derives every register value of one device from those three numbers
+ * plus the summation geometry, so "profiler parameters in -> CSR writes out" is one code path.
+ *   depth_levels = comparison levels D (leaves at level D); clusters K in {1,2,4,8}.
+ * regs_out[0..7] receive the values for registers 201..208 (single device, host node). */
+int dte_csr_from_profile(uint32_t n_trees, uint32_t depth_levels, uint32_t tuple_bytes,
+                         uint32_t clusters, uint32_t missing_value, uint64_t n_tuples,
+                         uint64_t regs_out[8]);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t num_trees;        /* trees resident on this device */
+    uint32_t num_levels;       /* D */
+    uint32_t num_features;     /* F = 4 * tuple_numcls */
+    uint32_t clusters;         /* K */
+    uint32_t trees_per_pu;     /* S */
+    uint32_t kernel_variant;   /* which walk kernel dte_infer_* will launch (dte_kernel_variant) */
+    uint32_t tuples_per_cta;   /* tuple tile held in shared memory by one CTA */
+    uint32_t sm_count;
+    uint64_t ensemble_bytes;   /* device bytes of the repacked ensemble */
+    uint64_t kernel_launches;  /* walk-kernel launches since create */
+    double   last_walk_ms;     /* device time of the most recent walk launch(es) of one infer call */
+} dte_info;
+int dte_get_info(dte_t* engine, dte_info* info);
+
+typedef enum {
+    DTE_KERNEL_AUTO = 0,
+    DTE_KERNEL_GENERIC = 1,    /* one thread per tuple, everything from global memory (any F, any D) */
+    DTE_KERNEL_TILE = 2,       /* feature-major tuple tile in shared memory, nodes read through L1/L2 */
+    DTE_KERNEL_TILE_STAGED = 3 /* + upper tree levels staged into shared memory by bulk async copies */
+} dte_kernel_variant;
+/* Test/benchmark hook: force a kernel variant (DTE_KERNEL_AUTO restores the default choice). */
+int dte_set_kernel_variant(dte_t* engine, int variant);
+
+/* ---- benchmark support: synthetic tuples generated on the device ---------------------------- */
+/* tuple i, feature f = U[0,1) from SplitMix64(seed, i*F+f), replaced by `missing_value` with
+ * probability missing_ppm/1e6.  tests/ and bench.py regenerate any sample of it on the host. */
+int dte_synth_tuples_device(dte_t* engine, void* d_tuples, uint64_t first_tuple, uint64_t n,
+                            uint32_t num_features, uint64_t seed, uint32_t missing_ppm,
+                            uint32_t missing_value, void* cuda_stream);
+
+const char* dte_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
