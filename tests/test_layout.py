@@ -1,0 +1,66 @@
+"""Host-side layout logic: stream packing, synthetic generators, sharding arithmetic."""
+import numpy as np
+
+import ddt_b200 as ddt
+
+L, S = ddt.layout, ddt.sharding
+
+
+def test_tree_cls_formula():
+    assert L.tree_cls(4) == (8, 2) and L.tree_cls(12) == (2048, 512) and L.tree_cls(8) == (128, 32)
+    assert L.tree_cls(1) == (1, 1) and L.tree_cls(2) == (2, 1) and L.tree_cls(3) == (4, 1)
+    for d in range(3, 13):                       # 10 * 2^D bytes per tree for D >= 3
+        w, f = L.tree_cls(d)
+        assert (w + f) * 16 == 10 * 2 ** d
+
+
+def test_pack_unpack_roundtrip_and_word_order():
+    W, FI = L.synth_ensemble(5, 3, 16)
+    wl, fl = L.pack_streams(W, FI, 3)
+    assert wl.shape == (5 * 4, 4) and fl.shape == (5 * 1, 8)
+    # little-endian: word i of a line at byte offset 4i, index i at byte offset 2i (PipelinedMUX.sv:63-65)
+    raw = wl.tobytes()
+    assert int.from_bytes(raw[4:8], "little") == int(W[0, 1])
+    assert int.from_bytes(fl.tobytes()[2:4], "little") == int(FI[0, 1])
+    W2, FI2 = L.unpack_streams(wl, fl, 3)
+    assert (W2 == W).all() and (FI2 == FI).all()
+    # padding words are zero
+    assert wl.reshape(5, 16)[:, 15].sum() == 0 and fl.reshape(5, 8)[:, 7].sum() == 0
+
+
+def test_synth_is_deterministic_and_in_contract():
+    a = L.synth_tuples(100, 50, 32)
+    b = L.synth_tuples(0, 200, 32)[100:150]
+    assert (a == b).all()                        # counter based: any window regenerates identically
+    v = a.view(np.float32)
+    miss = a == L.MISSING_DEFAULT
+    assert ((v >= 0) & (v < 1))[~miss].all()
+    m = L.synth_tuples(0, 4000, 64, missing_ppm=50000)
+    frac = (m == L.MISSING_DEFAULT).mean()
+    assert 0.04 < frac < 0.06
+    W, FI = L.synth_ensemble(32, 6, 40)
+    assert ((FI & 0x7FF) < 40).all() and (FI & 0x4000).sum() == 0 and 0 < ((FI >> 13) & 1).mean() < 1
+    leaves = W[:, 63:].view(np.float32)
+    assert np.isfinite(leaves).all() and (np.abs(leaves) < 2.0 / 32).all()
+    # golden pin of the generator itself
+    assert int(L.splitmix64(0, np.arange(1, dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
+
+
+def test_result_lines_drop_partial_line():
+    s = np.arange(10, dtype=np.float32)
+    r = L.result_lines(s)
+    assert r.shape == (2, 4) and r[1, 3] == 7.0
+
+
+def test_sharding_arithmetic():
+    assert [S.ensemble_chunk(8192, g, 8) for g in range(8)] == [(1024 * g, 1024) for g in range(8)]
+    chunks = [S.ensemble_chunk(10, g, 4) for g in range(4)]
+    assert chunks == [(0, 3), (3, 3), (6, 3), (9, 1)]
+    assert sum(c for _, c in chunks) == 10
+    shards = [S.data_shard(10, g, 4) for g in range(4)]
+    assert shards == [(0, 3), (3, 3), (6, 2), (8, 2)]
+    assert S.shard_geometry(8192, 10, 8, 8) == (8, 16)
+    deal = S.deal_batches(10, 4, 3)
+    assert deal == [[(0, 4)], [(4, 4)], [(8, 2)]]
+    deal = S.deal_batches(20, 4, 2)
+    assert deal[0] == [(0, 4), (8, 4), (16, 4)] and deal[1] == [(4, 4), (12, 4)]
