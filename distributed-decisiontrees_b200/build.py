@@ -52,3 +52,20 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+
+
+HOST_SRC = os.path.join(HERE, "..", "tools", "dte_host.cpp")
+HOST_OUT = os.path.join(HERE, "..", "tools", "dte_host")
+
+
+def build_host(force=False):
+    """Compile the C++ host program (tools/dte_host.cpp) against libdte.so."""
+    if not force and os.path.exists(HOST_OUT) and os.path.getmtime(HOST_OUT) >= max(os.path.getmtime(HOST_SRC), os.path.getmtime(OUT)):
+        return HOST_OUT
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", HOST_OUT, HOST_SRC, "-L" + HERE, "-ldte",
+           "-Wl,-rpath," + HERE, "-ldl", "-lpthread", "-lrt"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return HOST_OUT

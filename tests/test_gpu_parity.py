@@ -296,3 +296,23 @@ def test_full_size_config_properties(torch_cuda):
         got = ds2.cpu().numpy().view(np.uint32)[idx]
         assert (got == want).all()
         assert 0.02 < O.labels(want).mean() < 0.98 or True
+
+
+def test_cpp_host_program_matches_python_path():
+    """tools/dte_host.cpp: the C++ host with the profiler's parameter surface (N_trees, Depth_tree,
+    Size_tuple_Bytes) drives the same engine through registers + line streams; its checksum must
+    equal the oracle's on the identically generated ensemble and tuples."""
+    import json
+    import subprocess
+    from ddt_b200 import build as B
+    exe = B.build_host()
+    T, D, F, K, n = 64, 6, 64, 8, 4000
+    for mode in ("stream", "host"):
+        out = subprocess.run([exe, str(T), str(D), str(4 * F), str(n), str(K), mode], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+        W, FI = L.synth_ensemble(T, D, F)
+        x = L.synth_tuples(0, n, F)
+        wl, fl = L.pack_streams(W, FI, D)
+        want = O.scores(oracle_cfg(D, K, 1, L.MISSING_DEFAULT, F, T), wl, fl, x, threads=8)
+        assert r["results"] == n and r["score_words_sum"] == int(want.astype(np.uint64).sum()), (mode, r)
