@@ -75,6 +75,12 @@ __device__ __forceinline__ uint4 ldg128_nc(const void* p) {
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+// 256-bit load (sm_100+: LDG.E.256): one instruction, one sector per lane for the bottom records
+__device__ __forceinline__ void ldg256_nc(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
 __device__ __forceinline__ uint4 ldg128_stream(const void* p) {   // tuples: read once, keep out of L1
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -136,19 +142,19 @@ __device__ __forceinline__ void acc_set(float (&a)[8], uint32_t j, float v) {
 //       meta = fidx | missing_right<<16
 // FEAT(f) fetches feature f of this lane's tuple.
 // ---------------------------------------------------------------------------------------------
-template <bool WIDE> struct BotRec {
-    uint4 a, b, c;
-};
-template <bool WIDE> __device__ __forceinline__ void bot_load(BotRec<WIDE>& r, const uint4* rec) {
-    r.a = ldg128_nc(rec);
-    r.b = ldg128_nc(rec + 1);
-    if (WIDE) r.c = ldg128_nc(rec + 2);
+template <bool WIDE> struct BotRec;
+template <> struct BotRec<false> { uint4 a, b; };
+template <> struct BotRec<true> { uint4 a, b, c; };
+__device__ __forceinline__ void bot_load(BotRec<false>& r, const uint4* rec) { ldg256_nc(rec, r.a, r.b); }
+__device__ __forceinline__ void bot_load(BotRec<true>& r, const uint4* rec) {
+    ldg256_nc(rec, r.a, r.b);
+    r.c = ldg128_nc(rec + 2);
 }
 template <bool WIDE, class Feat>
 __device__ __forceinline__ float bot_finish(const BotRec<WIDE>& r, uint32_t missing, Feat feat) {
     uint32_t fp, fl, fr, mp, ml, mr;
     uint4 leaves;
-    if (WIDE) {
+    if constexpr (WIDE) {
         fp = r.a.w & 0xFFFFu; mp = r.a.w >> 16;
         fl = r.b.x & 0xFFFFu; ml = r.b.x >> 16;
         fr = r.b.y & 0xFFFFu; mr = r.b.y >> 16;
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(128) dt_walk_generic(const WalkParams p) {
             }
             const uint32_t j = (o >> 3) - (p.nb - 1);
             BotRec<WIDE> br;
-            bot_load<WIDE>(br, p.bottom + ((size_t)t * p.nb + j) * BV);
+            bot_load(br, p.bottom + ((size_t)t * p.nb + j) * BV);
             float leaf = bot_finish<WIDE>(br, p.missing, feat);
             // static register index for l[q]
 #pragma unroll
@@ -320,12 +326,37 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
         for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
         float half0 = 0.0f;
 
-        for (uint32_t q = 0; q < steps; ++q) {
+        // finish one step: resolve the ILP bottom records into leaves, tree8-reduce, accumulate in the
+        // reference's order.  Called one step late so the record fetch overlaps the next top walk.
+        auto finish = [&](const BotRec<WIDE> (&rec)[ILP], uint32_t qf) {
+            float l[ILP];
+#pragma unroll
+            for (int c = 0; c < ILP; ++c) l[c] = bot_finish<WIDE>(rec[c], p.missing, feat);
+            float r;
+            bool group_done;
+            if constexpr (ILP == 8) {
+                r = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
+                             fadd_ref(fadd_ref(l[4], l[5]), fadd_ref(l[6], l[7])));
+                group_done = true;
+            } else {
+                float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
+                group_done = (qf & 1u) != 0;
+                r = fadd_ref(half0, h);
+                half0 = h;
+            }
+            if (group_done) {
+                const uint32_t j = (qf / (8 / ILP)) % p.K;
+                acc_set(acc, j, fadd_ref(r, acc_get(acc, j)));
+            }
+        };
+
+        // one step, first half: walk the top levels of trees [q*ILP, q*ILP+ILP) and ISSUE the loads of
+        // their bottom records into `dst` (not consumed here)
+        auto walk_top = [&](uint32_t q, BotRec<WIDE> (&dst)[ILP]) {
             const uint32_t t0 = q * ILP;
             uint32_t o[ILP];
 #pragma unroll
             for (int c = 0; c < ILP; ++c) o[c] = 0;
-
             if (STAGED) {
                 mbar_wait(sbase + 8 * slot, par);
                 const uint32_t tb = sbase + kBarBytes + slot * stage_bytes;
@@ -355,34 +386,32 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
                     for (int c = 0; c < ILP; ++c) o[c] = 2 * o[c] + step_inc(xv[c], nd[c].x, nd[c].y, p.missing);
                 }
             }
-
-            // ---- bottom: last two comparison levels + leaves, one 32 B (64 B) record per walk ----
-            BotRec<WIDE> br[ILP];
+            // bottom: last two comparison levels + leaves, ONE 32 B (64 B) record per walk
 #pragma unroll
             for (int c = 0; c < ILP; ++c) {
                 const uint32_t j = (o[c] >> 3) - (p.nb - 1);
-                bot_load<WIDE>(br[c], p.bottom + ((size_t)(t0 + c) * p.nb + j) * BV);
+                bot_load(dst[c], p.bottom + ((size_t)(t0 + c) * p.nb + j) * BV);
             }
-            float l[ILP];
-#pragma unroll
-            for (int c = 0; c < ILP; ++c) l[c] = bot_finish<WIDE>(br[c], p.missing, feat);
+        };
 
-            // ---- tree8 reduce + accumulation in the reference's order ----
-            float r;
-            bool group_done;
-            if constexpr (ILP == 8) {
-                r = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
-                             fadd_ref(fadd_ref(l[4], l[5]), fadd_ref(l[6], l[7])));
-                group_done = true;
-            } else {
-                float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
-                group_done = (q & 1u) != 0;
-                r = fadd_ref(half0, h);
-                half0 = h;
+        // Software pipeline with two register buffers (no copies): the records issued by step q are
+        // consumed after the top walk of step q+1, so their L2 latency hides behind shared-memory work.
+        BotRec<WIDE> recA[ILP], recB[ILP];
+        if (steps > 0) {
+            walk_top(0, recA);
+            uint32_t q = 1;
+            for (; q + 1 < steps; q += 2) {
+                walk_top(q, recB);
+                finish(recA, q - 1);
+                walk_top(q + 1, recA);
+                finish(recB, q);
             }
-            if (group_done) {
-                const uint32_t j = (q / (8 / ILP)) % p.K;
-                acc_set(acc, j, fadd_ref(r, acc_get(acc, j)));
+            if (q < steps) {
+                walk_top(q, recB);
+                finish(recA, q - 1);
+                finish(recB, q);
+            } else {
+                finish(recA, q - 1);
             }
         }
 
