@@ -279,18 +279,23 @@ Plan make_plan(const dte_engine* e) {
     };
     int want = e->forced_variant;
     const bool can_stage = e->Dtop >= 3;          // below that there is nothing worth staging
-    // staged candidates, best first
-    const int cand[3][2] = {{4, 3}, {8, 2}, {4, 2}};
+    // staged candidates {ILP, ring stages}: most walks in flight (ILP x warps) wins, then the deeper
+    // ring.  Measured on B200 (profiles/r01_sweeps.md): 8 trees x 5 warps with a single 64 KiB stage
+    // beats 4 x 5 double-buffered — walks in flight matter more than hiding the ring refill.
+    const int cand[4][2] = {{8, 1}, {8, 2}, {4, 2}, {4, 1}};
     Plan staged;
     if (can_stage) {
+        int best = 0;
         for (auto& c : cand) {
             int ilp = e->tune.ilp ? e->tune.ilp : c[0];
             int st = e->tune.stages ? e->tune.stages : c[1];
             if (ilp != 4 && ilp != 8) ilp = 4;
-            st = std::max(2, std::min(st, 8));
+            st = std::max(1, std::min(st, 8));
             int w = max_warps(ilp, st);
             if (e->tune.warps) w = std::min(w, e->tune.warps);
-            if (w > staged.nwarps) {
+            const int score = w * ilp * 8 + st;
+            if (w >= 1 && score > best) {
+                best = score;
                 staged.variant = DTE_KERNEL_TILE_STAGED;
                 staged.ilp = ilp; staged.nstages = st; staged.nwarps = w; staged.wide = e->wide;
                 staged.smem = tile_smem(F, w, ilp, st, e->top_stride);
