@@ -69,3 +69,18 @@ def build_host(force=False):
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
     return HOST_OUT
+
+
+MODEL_SRC = os.path.join(HERE, "..", "tools", "dte_model.cpp")
+MODEL_OUT = os.path.join(HERE, "..", "tools", "dte_model")
+
+
+def build_model(force=False):
+    """Compile the closed-form performance model CLI (tools/dte_model.cpp; no CUDA needed)."""
+    if not force and os.path.exists(MODEL_OUT) and os.path.getmtime(MODEL_OUT) >= os.path.getmtime(MODEL_SRC):
+        return MODEL_OUT
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    res = subprocess.run([gxx, "-O2", "-std=c++17", "-o", MODEL_OUT, MODEL_SRC], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return MODEL_OUT

@@ -58,7 +58,11 @@ struct dte_engine {
     // ---- stream state (PCIeReceiver.sv FSM) ----
     enum { ST_IDLE = 0, ST_TREES = 1, ST_WAIT = 2, ST_DATA = 3 } state = ST_IDLE;
     uint64_t lines_received = 0;
-    std::vector<unsigned char> tree_lines;      // weights then findexes, as received
+    uint32_t node_index = 0;                    // position in devices_list; 0 = host node (PCIeReceiver.sv:160-178)
+    uint64_t cur_w = 0, cur_f = 0, cur_d = 0;   // currWCount / currFCount / currDCount
+    uint32_t cur_dev = 0;                       // currDevID
+    uint64_t local_w_lines = 0;                 // weight lines kept by this node
+    std::vector<unsigned char> tree_lines;      // weights then findexes kept by this node, as received
     std::vector<unsigned char> tuple_partial;   // bytes of an incomplete tuple
     std::vector<float> result_words;            // scores not yet returned, tuple order
     size_t result_read_pos = 0;                 // words already handed out
@@ -517,6 +521,9 @@ int dte_softreg_write(dte_t* e, uint32_t addr, uint64_t data) {
     // `start` (EngineCSR.sv:191-193): Core FSM, counters and schedules reset (Core.sv:168-187);
     // the PU tree memories are NOT cleared (DTPU.sv:307-319) -> the resident ensemble stays.
     e->lines_received = 0;
+    e->cur_w = e->cur_f = e->cur_d = 0;
+    e->cur_dev = 0;
+    e->local_w_lines = 0;
     e->tree_lines.clear();
     e->tuple_partial.clear();
     e->result_words.clear();
@@ -565,22 +572,74 @@ int dte_stream_write(dte_t* e, const void* cl128, size_t n_lines) {
             if (total == 0 || wtotal == 0 || wtotal >= total)
                 return fail(e, DTE_ERR_CONFIG, "reg 202: total_num_trees_cls=%llu total_num_weights_cls=%llu",
                             (unsigned long long)total, (unsigned long long)wtotal);
+            // Multi-node chunking (PCIeReceiver.sv:241-264): unless broadcast_trees, the weights stream
+            // is cut every numcls_local_weights lines and the index stream every numcls_local_findexes
+            // lines, chunk i going to devices_list[i % numDevs]; entry 0 is the host node itself
+            // (:160-178).  Every process replays the SAME stream; engine g keeps the chunks of entry g.
+            const uint64_t r201 = e->regs[1], r203 = e->regs[3];
+            const bool multi = (r201 >> 5) & 1, bcast_trees = (r201 >> 3) & 1;
+            const uint64_t chunk_w = (r203 & 0xFFFF) + 1, chunk_f = (r203 >> 16) & 0xFFFF;
+            const uint32_t ndev = (uint32_t)std::max<uint64_t>(1, (r203 >> 32) & 0xFF);
+            const bool deal = multi && !bcast_trees && ndev > 1;
+            if (deal && (chunk_f == 0 || e->node_index >= ndev))
+                return fail(e, DTE_ERR_CONFIG, "reg 203: numcls_local_findexes=%llu numDevs=%u node=%u",
+                            (unsigned long long)chunk_f, ndev, e->node_index);
             const size_t take = (size_t)std::min<uint64_t>(n_lines, total - e->lines_received);
-            e->tree_lines.insert(e->tree_lines.end(), p, p + take * 16);
+            if (!deal) {
+                e->tree_lines.insert(e->tree_lines.end(), p, p + take * 16);
+                e->local_w_lines += std::min<uint64_t>(take, wtotal > e->lines_received ? wtotal - e->lines_received : 0);
+            } else {
+                for (size_t i = 0; i < take; ++i) {
+                    const bool is_w = e->lines_received + i < wtotal;
+                    if (e->cur_dev == e->node_index) {
+                        e->tree_lines.insert(e->tree_lines.end(), p + i * 16, p + i * 16 + 16);
+                        if (is_w) e->local_w_lines++;
+                    }
+                    uint64_t& cnt = is_w ? e->cur_w : e->cur_f;
+                    if (++cnt == (is_w ? chunk_w : chunk_f)) {
+                        cnt = 0;
+                        e->cur_dev = (e->cur_dev + 1 == ndev) ? 0 : e->cur_dev + 1;
+                    }
+                    if (is_w && e->lines_received + i + 1 == wtotal) { e->cur_dev = 0; e->cur_w = 0; }   // index stream restarts at the host
+                }
+            }
             e->lines_received += take;
             p += take * 16;
             n_lines -= take;
             if (e->lines_received == total) {
                 // prog_mode = (numcls_received < total_num_weights_cls), PCIeReceiver.sv:136-139
-                int rc = load_ensemble(e, e->tree_lines.data(), (size_t)wtotal, e->tree_lines.data() + wtotal * 16,
-                                       (size_t)(total - wtotal), 0, 0);
+                const size_t lw = (size_t)e->local_w_lines, lf = e->tree_lines.size() / 16 - lw;
+                int rc = (lw && lf) ? load_ensemble(e, e->tree_lines.data(), lw, e->tree_lines.data() + lw * 16, lf, 0, 0)
+                                    : fail(e, DTE_ERR_CONFIG, "node %u received no trees", e->node_index);
                 e->tree_lines.clear();
                 e->tree_lines.shrink_to_fit();
                 if (rc) { e->state = dte_engine::ST_IDLE; return rc; }
                 e->state = dte_engine::ST_DATA;                                 // WAIT_DATA -> RECEIVE_DATA
+                e->cur_dev = 0;
+                e->cur_d = 0;
             }
         } else if (e->state == dte_engine::ST_DATA) {
             const size_t tbytes = (size_t)e->tuple_cls * 16;
+            // Data dealing (PCIeReceiver.sv:298-307): unless broadcast_data, batches of core_data_batch_cls
+            // lines go round-robin over devices_list; this engine keeps the batches of its own entry.
+            const uint64_t r201d = e->regs[1];
+            const bool multi_d = (r201d >> 5) & 1, bcast_data = (r201d >> 2) & 1, distributed = r201d & 1;
+            const uint32_t ndev_d = (uint32_t)std::max<uint64_t>(1, (e->regs[3] >> 32) & 0xFF);
+            std::vector<unsigned char> mine;
+            const size_t lines_in = n_lines;
+            if (multi_d && !bcast_data && !distributed && ndev_d > 1) {
+                const uint64_t batch = r201d >> 32;
+                if (batch == 0 || batch % e->tuple_cls)
+                    return fail(e, DTE_ERR_CONFIG, "reg 201: core_data_batch_cls=%llu must be a positive multiple of tuple_numcls=%u",
+                                (unsigned long long)batch, e->tuple_cls);
+                mine.reserve(n_lines * 16 / ndev_d + 16);
+                for (size_t i = 0; i < n_lines; ++i) {
+                    if (e->cur_dev == e->node_index) mine.insert(mine.end(), p + i * 16, p + i * 16 + 16);
+                    if (++e->cur_d == batch) { e->cur_d = 0; e->cur_dev = (e->cur_dev + 1 == ndev_d) ? 0 : e->cur_dev + 1; }
+                }
+                p = mine.data();
+                n_lines = mine.size() / 16;
+            }
             // frame tuples by counting tuple_numcls lines (InputDistributor.sv:276-296)
             std::vector<unsigned char>& part = e->tuple_partial;
             const unsigned char* src = p;
@@ -594,7 +653,7 @@ int dte_stream_write(dte_t* e, const void* cl128, size_t n_lines) {
                 nbytes = joined.size();
             }
             const size_t ntup = nbytes / tbytes;
-            e->lines_received += n_lines;
+            e->lines_received += lines_in;
             if (ntup) {
                 const size_t old = e->result_words.size();
                 e->result_words.resize(old + ntup);
@@ -737,6 +796,12 @@ int dte_get_info(dte_t* e, dte_info* info) {
         info->kernel_variant = (uint32_t)pl.variant;
         info->tuples_per_cta = pl.variant == DTE_KERNEL_GENERIC ? 128u : 32u * (uint32_t)pl.nwarps;
     }
+    return DTE_OK;
+}
+
+int dte_set_node(dte_t* e, uint32_t node_index) {
+    if (!e || node_index > 19) return DTE_ERR_ARG;             // devices_list has 20 entries (EngineCSR.sv:250-296)
+    e->node_index = node_index;
     return DTE_OK;
 }
 

@@ -36,6 +36,7 @@ ABI = [
     ("dte_csr_from_profile", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _u64p]),
     ("dte_get_info", C.c_int, [C.c_void_p, C.c_void_p]),
     ("dte_set_kernel_variant", C.c_int, [C.c_void_p, C.c_int]),
+    ("dte_set_node", C.c_int, [C.c_void_p, C.c_uint32]),
     ("dte_synth_tuples_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
                                            C.c_uint32, C.c_uint32, C.c_void_p]),
     ("dte_version", C.c_char_p, []),
@@ -222,6 +223,10 @@ class Engine:
         self._check(self._lib.dte_synth_tuples_device(self._h, _ptr(d_tuples), int(first_tuple), int(n), int(num_features),
                                                       int(seed), int(missing_ppm), int(missing_value),
                                                       _ptr(stream) if stream else None))
+
+    def set_node(self, node_index):
+        """Entry of devices_list this engine stands for (0 = host node)."""
+        self._check(self._lib.dte_set_node(self._h, int(node_index)))
 
     def set_kernel_variant(self, variant):
         self._check(self._lib.dte_set_kernel_variant(self._h, int(variant)))

@@ -54,6 +54,16 @@ const char* dte_last_error(const dte_t* engine);
 int dte_softreg_write(dte_t* engine, uint32_t addr, uint64_t data);
 int dte_softreg_read(dte_t* engine, uint32_t addr, uint64_t* data);
 
+/* Which entry of devices_list (registers 208-210) this engine is; 0 = the host node (default).
+ * Replaces the FPGA's position on the ring: with multiple_nodes=1 (reg 201[5]) the receiver cuts
+ * the tree streams into per-device chunks of numcls_local_weights / numcls_local_findexes lines
+ * (reg 203) unless broadcast_trees, and deals data batches of core_data_batch_cls lines (reg
+ * 201[63:32]) round-robin unless broadcast_data (rtl/DTEngine/PCIeReceiver.sv:160-178,241-264,
+ * 298-307).  One process per GPU replays the SAME stream into its engine; engine g keeps what the
+ * ring would have delivered to device g.  Results: aggregate mode -> partial scores (combine with
+ * one NCCL reduce / dte_ring_add_device); otherwise -> the scores of the local tuples, local order. */
+int dte_set_node(dte_t* engine, uint32_t node_index);
+
 /* ---- PCIe line streams --------------------------------------------------------------------- */
 /* Replaces the PCIe DMA input stream of slot >= 1 (rtl/PCIeShim.sv:99-100,124-141) in the order
  * rtl/DTEngine/PCIeReceiver.sv:136-139,205-316 consumes it after `start`:

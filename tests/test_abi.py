@@ -21,7 +21,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol():
     lib = ddt.load_library()
     syms = header_symbols()
-    assert len(syms) >= 18
+    assert len(syms) >= 19
     for s in syms:
         assert hasattr(lib, s), "libdte.so does not export %s" % s
     # and the Python mirror binds exactly the header's set
@@ -78,6 +78,7 @@ def test_null_arguments_are_errors_not_crashes():
     v = C.c_uint64()
     assert lib.dte_softreg_read(None, 220, C.byref(v)) == -1
     assert lib.dte_last_error(None) == b"null engine"
+    assert lib.dte_set_node(None, 0) == -1
 
 
 def test_product_does_not_touch_the_oracle():

@@ -316,3 +316,70 @@ def test_cpp_host_program_matches_python_path():
         wl, fl = L.pack_streams(W, FI, D)
         want = O.scores(oracle_cfg(D, K, 1, L.MISSING_DEFAULT, F, T), wl, fl, x, threads=8)
         assert r["results"] == n and r["score_words_sum"] == int(want.astype(np.uint64).sum()), (mode, r)
+
+
+def _multi_node_regs(T, D, F, K, n, ndev, mode, batch_tuples=2):
+    """Register values of a multi-device run as a Catapult host would write them (EngineCSR.sv:194-216)."""
+    w_cls, f_cls = L.tree_cls(D)
+    per = -(-T // ndev)
+    regs = E.csr_from_profile(T, D, 4 * F, K, L.MISSING_DEFAULT, n)
+    flags = 0x2 | 0x20 | 0x40                       # host_node | multiple_nodes | pcie_receiver_enabled
+    if mode == "ensemble":
+        flags |= 0x4 | 0x10                         # broadcast_data | aggreg_enabled
+        S = -(-per // (8 * K))
+        regs[205] = (regs[205] & ~(0xFF << 36)) | (S << 36)
+    else:
+        flags |= 0x8                                # broadcast_trees
+    regs[201] = flags | ((batch_tuples * (F // 4)) << 32)
+    regs[203] = ((per * w_cls - 1) & 0xFFFF) | ((per * f_cls) << 16) | (ndev << 32)
+    return regs
+
+
+@pytest.mark.parametrize("mode", ["ensemble", "data"])
+def test_multi_node_stream_partitioning(mode, torch_cuda):
+    """N1: every 'device' (engine) replays the SAME line stream and keeps what PCIeReceiver would have
+    sent it: tree chunks by numcls_local_weights/findexes (PCIeReceiver.sv:241-264) or data batches of
+    core_data_batch_cls lines (:298-307)."""
+    torch = torch_cuda
+    T, D, F, K, n, ndev = 48, 5, 32, 2, 404, 3
+    W, FI = L.synth_ensemble(T, D, F, seed=41)
+    x = L.synth_tuples(0, n, F, seed=42)
+    wl, fl = L.pack_streams(W, FI, D)
+    stream = np.concatenate([wl.view(np.uint8).reshape(-1, 16), fl.view(np.uint8).reshape(-1, 16), x.view(np.uint8).reshape(-1, 16)])
+    regs = _multi_node_regs(T, D, F, K, n, ndev, mode)
+    outs = []
+    for g in range(ndev):
+        with ddt.Engine(0) as e:
+            e.set_node(g)
+            for a, v in sorted(regs.items()):
+                e.softreg_write(a, v)
+            e.start()
+            for pos in range(0, stream.shape[0], 997):
+                e.stream_write(stream[pos:pos + 997])
+            outs.append(e.stream_read(1 << 20).reshape(-1).view(np.uint32).copy())
+            assert e.info()["num_trees"] == (T // ndev if mode == "ensemble" else T)
+    if mode == "ensemble":
+        parts = []
+        for g in range(ndev):
+            first, count = ddt.sharding.ensemble_chunk(T, g, ndev)
+            cw, cf = L.pack_streams(W[first:first + count], FI[first:first + count], D)
+            S = -(-count // (8 * K))
+            parts.append(O.scores(oracle_cfg(D, K, S, L.MISSING_DEFAULT, F, count), cw, cf, x))
+        for g in range(ndev):
+            assert (outs[g] == parts[g][: (n // 4) * 4]).all()
+        # ring combine of the engines' partials on the device == the oracle's ring order
+        with ddt.Engine(0) as e:
+            acc = torch.from_numpy(outs[0].view(np.float32).copy()).cuda()
+            for g in range(1, ndev):
+                nxt = torch.from_numpy(outs[g].view(np.float32).copy()).cuda()
+                e.ring_add_device(nxt, acc, acc, acc.numel(), stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            want = O.ring_combine([p[: (n // 4) * 4] for p in parts])
+            assert (acc.cpu().numpy().view(np.uint32) == want).all()
+    else:
+        full = O.scores(oracle_cfg(D, K, -(-T // (8 * K)), L.MISSING_DEFAULT, F, T), wl, fl, x)
+        deal = ddt.sharding.deal_batches(n * (F // 4), 2 * (F // 4), ndev)
+        for g in range(ndev):
+            idx = np.concatenate([np.arange(a // (F // 4), (a + c) // (F // 4)) for a, c in deal[g]])
+            want = full[idx]
+            assert (outs[g] == want[: (idx.size // 4) * 4]).all()

@@ -64,3 +64,20 @@ def test_sharding_arithmetic():
     assert deal == [[(0, 4)], [(4, 4)], [(8, 2)]]
     deal = S.deal_batches(20, 4, 2)
     assert deal[0] == [(0, 4), (8, 4), (16, 4)] and deal[1] == [(4, 4), (12, 4)]
+
+
+def test_performance_model_cli():
+    """tools/dte_model.cpp — the B200 counterpart of profiler/profiler.cpp; same three inputs."""
+    import re
+    import subprocess
+    from ddt_b200 import build as B
+    exe = B.build_model()
+    out = subprocess.run([exe, "512", "12", "128", "8"], capture_output=True, text=True)
+    assert out.returncode == 0
+    txt = out.stdout
+    # the reference's law f*Ncu*Npe/(depth*Ntrees) with 64 PEs at 150 MHz, D=12, 512 trees
+    m = re.search(r"engine\s*:\s*([0-9.e+]+) tuples/s per FPGA", txt)
+    assert m and abs(float(m.group(1)) - 150e6 * 64 / (12 * 512)) / (150e6 * 64 / (12 * 512)) < 1e-3
+    m = re.search(r"walk-bound\s*:\s*([0-9.e+]+)", txt)
+    assert m and float(m.group(1)) > 1e7
+    assert subprocess.run([exe], capture_output=True).returncode == 2
