@@ -122,6 +122,27 @@ __device__ __forceinline__ uint32_t step_inc(uint32_t x, uint32_t thr, uint32_t 
     return inc;
 }
 
+// Same decision as step_inc(), phrased on predicates so that only {compare, 3-input predicate LUT,
+// select} separate the feature value from the next node address: returns a_right if the walk goes
+// right (feature missing ? missing-goes-right flag : !(x < thr)), else a_left.
+__device__ __forceinline__ uint32_t step_select(uint32_t x, uint32_t thr, uint32_t meta, uint32_t missing,
+                                                uint32_t a_left, uint32_t a_right) {
+    uint32_t r;
+    asm("{\n\t"
+        ".reg .pred pge, pm, pmr, t1, t2, npm, pr;\n\t"
+        "setp.ge.s32 pge, %1, %2;\n\t"          // !(x < thr), signed compare of the raw words (DTPU.sv:655)
+        "setp.eq.u32 pm, %1, %3;\n\t"           // feature == missing pattern (DTPU.sv:653)
+        "setp.ge.u32 pmr, %4, 1048576;\n\t"     // meta >> 16 == 16  <=>  missing goes right (DTPU.sv:659)
+        "and.pred t1, pm, pmr;\n\t"
+        "not.pred npm, pm;\n\t"
+        "and.pred t2, npm, pge;\n\t"
+        "or.pred pr, t1, t2;\n\t"
+        "selp.u32 %0, %6, %5, pr;\n\t"
+        "}"
+        : "=r"(r) : "r"(x), "r"(thr), "r"(missing), "r"(meta), "r"(a_left), "r"(a_right));
+    return r;
+}
+
 // select partial `j` out of a register file of 8 (j is warp-uniform)
 __device__ __forceinline__ float acc_get(const float (&a)[8], uint32_t j) {
     float v = a[0];
@@ -360,16 +381,27 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
             if (STAGED) {
                 mbar_wait(sbase + 8 * slot, par);
                 const uint32_t tb = sbase + kBarBytes + slot * stage_bytes;
+                // Absolute shared-memory addresses: with A = tb_c + o the child address is
+                // A' = tb_c + 2o + 8 + 8*right = (2A + 8 - tb_c) + 8*right.  2A + (8 - tb_c) does not depend
+                // on the feature, so only {compare, select, add} sit between the feature and the next node.
+                uint32_t A[ILP], kb8[ILP];
+#pragma unroll
+                for (int c = 0; c < ILP; ++c) { A[c] = tb + c * tree_bytes; kb8[c] = 8u - A[c]; }
                 for (uint32_t lvl = 0; lvl < p.Dtop; ++lvl) {
                     uint2 nd[ILP];
                     uint32_t xv[ILP];
 #pragma unroll
-                    for (int c = 0; c < ILP; ++c) nd[c] = lds64(tb + c * tree_bytes + o[c]);
+                    for (int c = 0; c < ILP; ++c) nd[c] = lds64(A[c]);
 #pragma unroll
                     for (int c = 0; c < ILP; ++c) xv[c] = feat(nd[c].y & 0xFFFFu);
 #pragma unroll
-                    for (int c = 0; c < ILP; ++c) o[c] = 2 * o[c] + step_inc(xv[c], nd[c].x, nd[c].y, p.missing);
+                    for (int c = 0; c < ILP; ++c) {
+                        const uint32_t a2 = A[c] + A[c] + kb8[c];
+                        A[c] = step_select(xv[c], nd[c].x, nd[c].y, p.missing, a2, a2 + 8u);
+                    }
                 }
+#pragma unroll
+                for (int c = 0; c < ILP; ++c) o[c] = A[c] - (tb + c * tree_bytes);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sbase + 8 * (p.nstages + slot));
                 if (++slot == p.nstages) { slot = 0; par ^= 1; }
