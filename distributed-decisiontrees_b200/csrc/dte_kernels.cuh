@@ -387,19 +387,37 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
                 uint32_t A[ILP], kb8[ILP];
 #pragma unroll
                 for (int c = 0; c < ILP; ++c) { A[c] = tb + c * tree_bytes; kb8[c] = 8u - A[c]; }
-                for (uint32_t lvl = 0; lvl < p.Dtop; ++lvl) {
-                    uint2 nd[ILP];
-                    uint32_t xv[ILP];
+                // Skewed schedule inside the warp.  A walk step has three dependent stages:
+                //   S1 node record  = LDS.64 [A]            S2 feature = LDS [xs + fidx*row]
+                //   S3 compare + child address (ALU)
+                // Issuing all S1, then all S2, then all S3 (lock-step) leaves two shared-memory
+                // latencies per level exposed to an in-order warp.  Instead the ILP chains are split in
+                // two halves half a level apart: tick k issues S3+S1 of chain k and S2 of chain k+-H, so
+                // every load has H ticks (~H*12 instructions) of independent work before its first use.
+                // (The loads are `asm volatile`, so this program order IS the issue order.)
+                constexpr int H = ILP / 2;
+                uint2 nd[ILP];
+                uint32_t xv[ILP];
+                auto S1 = [&](int c) { nd[c] = lds64(A[c]); };
+                auto S2 = [&](int c) { xv[c] = feat(nd[c].y & 0xFFFFu); };
+                auto S3 = [&](int c) {
+                    const uint32_t a2 = A[c] + A[c] + kb8[c];
+                    A[c] = step_select(xv[c], nd[c].x, nd[c].y, p.missing, a2, a2 + 8u);
+                };
 #pragma unroll
-                    for (int c = 0; c < ILP; ++c) nd[c] = lds64(A[c]);
+                for (int c = 0; c < ILP; ++c) S1(c);                         // level 0 nodes
 #pragma unroll
-                    for (int c = 0; c < ILP; ++c) xv[c] = feat(nd[c].y & 0xFFFFu);
+                for (int c = 0; c < H; ++c) S2(c);                           // level 0 features, first half
+                for (uint32_t lvl = 0; lvl + 1 < p.Dtop; ++lvl) {
 #pragma unroll
-                    for (int c = 0; c < ILP; ++c) {
-                        const uint32_t a2 = A[c] + A[c] + kb8[c];
-                        A[c] = step_select(xv[c], nd[c].x, nd[c].y, p.missing, a2, a2 + 8u);
-                    }
+                    for (int k = 0; k < H; ++k) { S3(k); S1(k); S2(k + H); }         // S2(k+H) still at level lvl
+#pragma unroll
+                    for (int k = H; k < ILP; ++k) { S3(k); S1(k); S2(k - H); }       // S2(k-H) already at level lvl+1
                 }
+#pragma unroll
+                for (int k = 0; k < H; ++k) { S3(k); S2(k + H); }            // last staged level: no further node
+#pragma unroll
+                for (int k = H; k < ILP; ++k) S3(k);
 #pragma unroll
                 for (int c = 0; c < ILP; ++c) o[c] = A[c] - (tb + c * tree_bytes);
                 __syncwarp();
