@@ -199,6 +199,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     T, D, F, K = args.trees, args.depth, args.features, CLUSTERS
