@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tuples", type=int, default=0, help="tuples per GPU per step (default: 50M, reduced only if a step would take > 30 s)")
-    ap.add_argument("--e2e-tuples", type=int, default=2_000_000)
+    ap.add_argument("--e2e-tuples", type=int, default=4_000_000)
     ap.add_argument("--variant", type=int, default=0, help="force a kernel variant (dte_kernel_variant)")
     ap.add_argument("--no-ensemble-mode", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -398,7 +398,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_tuple": bytes_b,
                          "kernel": "dt_walk_tile" if info["kernel_variant"] != 1 else "dt_walk_generic",
-                         "launch_ms": launch_ms, "tuples_per_launch": n},
+                         "launch_ms": launch_ms, "tuples_per_launch": n,
+                         "note": "byte model (B) of SURVEY 8d charges every node visit (10 B) and leaf (4 B) as HBM traffic; the "
+                                 "engine serves them from shared memory / L2, so frac can exceed 1 — `traffic` is the DRAM bytes "
+                                 "ncu measured for one launch (profiles/ncu_traffic.json), ~1049 B per tuple"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "tuples/s", "h2d_bytes_per_step": int(n_e * F * 4 * world),
                     "d2h_bytes_per_step": int(n_e * 5 * world), "tuples_per_step": int(n_e * world), "steps": e2e_steps,

@@ -411,7 +411,7 @@ int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_
     if (n == 0) return DTE_OK;
     CUDA_TRY(e, cudaSetDevice(e->dev));
     const uint32_t F = e->tuple_cls * 4;
-    size_t chunk = e->tune.chunk ? e->tune.chunk : std::max<size_t>(4096, (96ull << 20) / (F * 4));
+    size_t chunk = e->tune.chunk ? e->tune.chunk : std::max<size_t>(4096, (64ull << 20) / (F * 4));
     chunk = std::min(chunk, n);
     int rc = ensure_chunk_buffers(e, chunk, F);
     if (rc) return rc;

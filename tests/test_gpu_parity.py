@@ -383,3 +383,37 @@ def test_multi_node_stream_partitioning(mode, torch_cuda):
             idx = np.concatenate([np.arange(a // (F // 4), (a + c) // (F // 4)) for a, c in deal[g]])
             want = full[idx]
             assert (outs[g] == want[: (idx.size // 4) * 4]).all()
+
+
+def test_randomised_geometry_stress():
+    """40 random (D, T, F, K, S, n, missing pattern) draws, every kernel variant, raw feature words
+    drawn from the FULL 32-bit space (NaN/Inf/negative/denormal patterns included — the comparator is
+    an integer compare, DTPU.sv:655, so every pattern is in contract for features and thresholds)."""
+    rng = np.random.default_rng(20260922)
+    for it in range(40):
+        D = int(rng.integers(1, 13))
+        K = int(rng.choice([1, 2, 4, 8]))
+        T = int(rng.integers(1, 70))
+        S = max(1, -(-T // (8 * K)) + int(rng.integers(-1, 2)))          # sometimes one slot short / long
+        F = 4 * int(rng.integers(1, 80))
+        n = int(rng.integers(1, 700))
+        W, FI = L.synth_ensemble(T, D, F, seed=int(rng.integers(1 << 40)))
+        n_int = (1 << D) - 1
+        # thresholds: arbitrary 32-bit words
+        W[:, :n_int] = rng.integers(0, 1 << 32, size=(T, n_int), dtype=np.uint64).astype(np.uint32)
+        x = rng.integers(0, 1 << 32, size=(n, F), dtype=np.uint64).astype(np.uint32)
+        missing = int(rng.integers(0, 1 << 32))
+        x[rng.random((n, F)) < 0.03] = missing
+        # make some features exactly equal to thresholds (the 'not smaller -> right' edge)
+        for _ in range(10):
+            t, i = int(rng.integers(T)), int(rng.integers(n_int))
+            x[int(rng.integers(n)), FI[t, i] & 0x7FF] = W[t, i]
+        check_case(W, FI, x, D, K, S, missing=missing)
+
+
+def test_deeper_than_rtl_limit():
+    # the CSR field allows D up to 15; beyond 12 the staged ring no longer fits and the planner falls back
+    D, T, F = 13, 8, 32
+    W, FI = L.synth_ensemble(T, D, F, seed=13)
+    x = L.synth_tuples(0, 300, F, seed=14)
+    check_case(W, FI, x, D, 1, 1)
