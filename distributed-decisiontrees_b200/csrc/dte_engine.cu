@@ -27,14 +27,14 @@ namespace {
 
 constexpr int kNumBuf = 3;   // device chunk buffers of the host-path pipeline
 
-struct Tune {               // experiment knobs, env DTE_TUNE="ilp=4,stages=3,warps=4,chunk=131072"
-    int ilp = 0, stages = 0, warps = 0;
+struct Tune {               // experiment knobs, env DTE_TUNE="ilp=4,pair=2,stages=1,warps=10,chunk=65536"
+    int ilp = 0, stages = 0, warps = 0, pair = 0;
     size_t chunk = 0;
 };
 
 struct Plan {               // how the next walk will be launched
     int variant = DTE_KERNEL_GENERIC;
-    int ilp = 8, nstages = 0, nwarps = 0;
+    int ilp = 8, pair = 1, nstages = 0, nwarps = 0;   // nwarps = consumer warps = groups * pair
     bool wide = false;
     size_t smem = 0;
 };
@@ -130,6 +130,7 @@ void parse_tune(Tune& t) {
             if (k == "ilp") t.ilp = (int)v;
             else if (k == "stages") t.stages = (int)v;
             else if (k == "warps") t.warps = (int)v;
+            else if (k == "pair") t.pair = (int)v;
             else if (k == "chunk") t.chunk = (size_t)v;
         }
         if (comma == std::string::npos) break;
@@ -267,8 +268,8 @@ int load_ensemble(dte_engine* e, const unsigned char* wl, size_t n_wl, const uns
 }
 
 // ---- launch planning ---------------------------------------------------------------------------
-size_t tile_smem(uint32_t F, int nwarps, int ilp, int nstages, uint32_t top_stride) {
-    return (size_t)kBarBytes + (size_t)nstages * ilp * top_stride * 8 + (size_t)F * 32 * nwarps * 4;
+size_t tile_smem(uint32_t F, int groups, int trees_per_stage, int nstages, uint32_t top_stride) {
+    return (size_t)kHdrBytes + (size_t)nstages * trees_per_stage * top_stride * 8 + (size_t)F * 32 * groups * 4;
 }
 
 Plan make_plan(const dte_engine* e) {
@@ -276,45 +277,48 @@ Plan make_plan(const dte_engine* e) {
     p.wide = e->wide;
     const uint32_t F = e->tuple_cls * 4;
     const size_t budget = (size_t)e->smem_optin;
-    auto max_warps = [&](int ilp, int nstages) -> int {
-        const size_t fixed = tile_smem(F, 0, ilp, nstages, e->top_stride);
+    // tuple groups (32 tuples, F*128 B of shared memory each) that fit next to the ring
+    auto max_groups = [&](int ilp, int pair, int nstages) -> int {
+        const size_t fixed = tile_smem(F, 0, ilp * pair, nstages, e->top_stride);
         if (fixed >= budget) return 0;
-        return (int)std::min<size_t>(8, (budget - fixed) / ((size_t)F * 128));
+        const int warp_cap = (ilp == 8) ? 8 : 12;            // __launch_bounds__ of dt_walk_tile (+1 producer warp)
+        int g = (int)std::min<size_t>((size_t)(warp_cap / pair), (budget - fixed) / ((size_t)F * 128));
+        if (e->tune.warps) g = std::min(g, std::max(1, e->tune.warps / pair));
+        return g;
     };
-    int want = e->forced_variant;
+    const int want = e->forced_variant;
     const bool can_stage = e->Dtop >= 3;          // below that there is nothing worth staging
-    // staged candidates {ILP, ring stages}: most walks in flight (ILP x warps) wins, then the deeper
-    // ring.  Measured on B200 (profiles/r01_sweeps.md): 8 trees x 5 warps with a single 64 KiB stage
-    // beats 4 x 5 double-buffered — walks in flight matter more than hiding the ring refill.
-    const int cand[4][2] = {{8, 1}, {8, 2}, {4, 2}, {4, 1}};
+    // staged candidates {trees per warp, warps per tuple group, ring stages}.  Measured on B200
+    // (profiles/r01_summary.md); the first candidate that fits with the most walks in flight wins.
+    const int cand[5][3] = {{4, 2, 1}, {8, 1, 1}, {8, 1, 2}, {4, 1, 2}, {4, 1, 1}};
     Plan staged;
     if (can_stage) {
         int best = 0;
         for (auto& c : cand) {
             int ilp = e->tune.ilp ? e->tune.ilp : c[0];
-            int st = e->tune.stages ? e->tune.stages : c[1];
+            int pair = e->tune.pair ? e->tune.pair : c[1];
+            int st = e->tune.stages ? e->tune.stages : c[2];
             if (ilp != 4 && ilp != 8) ilp = 4;
+            if (pair != 2 || ilp != 4) pair = (pair == 2 && ilp == 4) ? 2 : 1;
             st = std::max(1, std::min(st, 8));
-            int w = max_warps(ilp, st);
-            if (e->tune.warps) w = std::min(w, e->tune.warps);
-            const int score = w * ilp * 8 + st;
-            if (w >= 1 && score > best) {
+            const int g = max_groups(ilp, pair, st);
+            const int score = g * pair * ilp * 8 + (pair == 2 ? 4 : 0) + st;
+            if (g >= 1 && score > best) {
                 best = score;
                 staged.variant = DTE_KERNEL_TILE_STAGED;
-                staged.ilp = ilp; staged.nstages = st; staged.nwarps = w; staged.wide = e->wide;
-                staged.smem = tile_smem(F, w, ilp, st, e->top_stride);
+                staged.ilp = ilp; staged.pair = pair; staged.nstages = st; staged.nwarps = g * pair; staged.wide = e->wide;
+                staged.smem = tile_smem(F, g, ilp * pair, st, e->top_stride);
             }
-            if (e->tune.ilp && e->tune.stages) break;
+            if (e->tune.ilp && e->tune.stages && e->tune.pair) break;
         }
     }
     Plan tile;
     {
-        int ilp = (e->tune.ilp == 4) ? 4 : 8;
-        int w = max_warps(ilp, 0);
-        if (e->tune.warps) w = std::min(w, e->tune.warps);
-        if (w >= 1) {
-            tile.variant = DTE_KERNEL_TILE; tile.ilp = ilp; tile.nstages = 0; tile.nwarps = w; tile.wide = e->wide;
-            tile.smem = tile_smem(F, w, ilp, 0, e->top_stride);
+        const int ilp = (e->tune.ilp == 4) ? 4 : 8;
+        const int g = max_groups(ilp, 1, 0);
+        if (g >= 1) {
+            tile.variant = DTE_KERNEL_TILE; tile.ilp = ilp; tile.pair = 1; tile.nstages = 0; tile.nwarps = g; tile.wide = e->wide;
+            tile.smem = tile_smem(F, g, ilp, 0, e->top_stride);
         }
     }
     if (want == DTE_KERNEL_TILE_STAGED && staged.nwarps >= 1) return staged;
@@ -326,9 +330,9 @@ Plan make_plan(const dte_engine* e) {
     return p;
 }
 
-template <int ILP, bool STAGED, bool WIDE>
+template <int ILP, int P, bool STAGED, bool WIDE>
 cudaError_t launch_tile(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
-    auto k = dt_walk_tile<ILP, STAGED, WIDE>;
+    auto k = dt_walk_tile<ILP, P, STAGED, WIDE>;
     cudaError_t rc = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     k<<<grid, threads, smem, st>>>(wp);
@@ -366,20 +370,25 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
         else dt_walk_generic<false><<<(unsigned)blocks, threads, 0, st>>>(wp);
         rc = cudaGetLastError();
     } else {
-        const size_t M = 32ull * pl.nwarps;
+        const size_t M = 32ull * (pl.nwarps / pl.pair);
         const unsigned long long tiles = (n + M - 1) / M;
         if (tiles > 0xFFFFFFFFull) return fail(e, DTE_ERR_ARG, "batch too large for one launch");
         wp.tiles = (uint32_t)tiles;
         const int grid = (int)std::min<unsigned long long>(tiles, (unsigned long long)e->sm_count);
         const bool staged = pl.variant == DTE_KERNEL_TILE_STAGED;
         const int threads = 32 * (pl.nwarps + (staged ? 1 : 0));
+        const size_t sm = pl.smem;
+#define DTE_LAUNCH(ILP_, P_, ST_) (pl.wide ? launch_tile<ILP_, P_, ST_, true>(wp, grid, threads, sm, st) \
+                                           : launch_tile<ILP_, P_, ST_, false>(wp, grid, threads, sm, st))
         if (staged) {
-            if (pl.ilp == 8) rc = pl.wide ? launch_tile<8, true, true>(wp, grid, threads, pl.smem, st) : launch_tile<8, true, false>(wp, grid, threads, pl.smem, st);
-            else rc = pl.wide ? launch_tile<4, true, true>(wp, grid, threads, pl.smem, st) : launch_tile<4, true, false>(wp, grid, threads, pl.smem, st);
+            if (pl.ilp == 8) rc = DTE_LAUNCH(8, 1, true);
+            else if (pl.pair == 2) rc = DTE_LAUNCH(4, 2, true);
+            else rc = DTE_LAUNCH(4, 1, true);
         } else {
-            if (pl.ilp == 8) rc = pl.wide ? launch_tile<8, false, true>(wp, grid, threads, pl.smem, st) : launch_tile<8, false, false>(wp, grid, threads, pl.smem, st);
-            else rc = pl.wide ? launch_tile<4, false, true>(wp, grid, threads, pl.smem, st) : launch_tile<4, false, false>(wp, grid, threads, pl.smem, st);
+            if (pl.ilp == 8) rc = DTE_LAUNCH(8, 1, false);
+            else rc = DTE_LAUNCH(4, 1, false);
         }
+#undef DTE_LAUNCH
     }
     if (rc != cudaSuccess) return fail(e, DTE_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(rc));
     e->kernel_launches++;
@@ -794,7 +803,7 @@ int dte_get_info(dte_t* e, dte_info* info) {
     if (e->d_top) {
         Plan pl = make_plan(e);
         info->kernel_variant = (uint32_t)pl.variant;
-        info->tuples_per_cta = pl.variant == DTE_KERNEL_GENERIC ? 128u : 32u * (uint32_t)pl.nwarps;
+        info->tuples_per_cta = pl.variant == DTE_KERNEL_GENERIC ? 128u : 32u * (uint32_t)(pl.nwarps / pl.pair);
     }
     return DTE_OK;
 }

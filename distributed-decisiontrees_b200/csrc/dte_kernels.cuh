@@ -249,28 +249,42 @@ __global__ void __launch_bounds__(128) dt_walk_generic(const WalkParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel 2/3 — tile kernels.  Persistent CTAs (one per SM); CTA = nwarps consumer warps
-// (+ 1 producer warp when STAGED).  Shared memory:
+// Kernel 2/3 — tile kernels.  Persistent CTAs (one per SM).  A CTA holds G tuple groups of 32
+// tuples; each group is served by P consumer warps (P = 1 or 2) that share the group's tile
+// columns and split every stage of ILP*P trees between them (+ 1 producer warp when STAGED).
+// P = 2 doubles the warps per SM without costing shared memory — the tile, not the warp count,
+// is what fills the SM — so the hardware scheduler, not a static interleave, hides the
+// shared-memory latency.  Shared memory:
 //   [0,128)                       mbarriers: full[nstages], empty[nstages]
-//   [128, 128 + ring)             STAGED: nstages x ILP tree tops (ILP * top_stride * 8 B each)
-//   [.., + F * M * 4)             xs[f][M] feature-major tuple tile, M = 32 * nwarps columns
-// Warp w owns columns 32w..32w+31 exclusively, so tile reloads need no CTA-wide barrier.
+//   [128, 128+2048)               P = 2: half-sum exchange, [group][step parity][lane] fp32
+//   [kHdrBytes, + ring)           STAGED: nstages x (ILP*P) tree tops (top_stride * 8 B each)
+//   [.., + F * M * 4)             xs[f][M] feature-major tuple tile, M = 32 * G columns
+// Group g owns columns 32g..32g+31 exclusively, so tile reloads need no CTA-wide barrier.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kBarBytes = 128;
+constexpr uint32_t kXchBytes = 2048;
+constexpr uint32_t kHdrBytes = kBarBytes + kXchBytes;
 
-template <int ILP, bool STAGED, bool WIDE>
-__global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
+__device__ __forceinline__ void group_barrier(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int ILP, int P, bool STAGED, bool WIDE>
+__global__ void __launch_bounds__(ILP == 8 ? 288 : 416, 1) dt_walk_tile(const WalkParams p) {
+    static_assert(P == 1 || (P == 2 && ILP == 4), "a warp pair splits a tree8 group 4 + 4");
     constexpr int BV = WIDE ? 4 : 2;
+    constexpr int SP = ILP * P;                         // trees per ring stage / per step
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t M = 32u * p.nwarps;
+    const uint32_t G = p.nwarps / P;                    // tuple groups per CTA
+    const uint32_t M = 32u * G;
     const uint32_t tree_bytes = p.top_stride * 8u;
-    const uint32_t stage_bytes = (uint32_t)ILP * tree_bytes;
+    const uint32_t stage_bytes = (uint32_t)SP * tree_bytes;
     const uint32_t ring_bytes = STAGED ? p.nstages * stage_bytes : 0u;
-    const uint32_t xs_base = sbase + kBarBytes + ring_bytes;
+    const uint32_t xs_base = sbase + kHdrBytes + ring_bytes;
     const uint32_t row_bytes = M * 4u;
-    const uint32_t steps = p.groups * (8 / ILP);       // ILP trees per step
+    const uint32_t steps = p.groups * (8 / SP);         // SP trees per step
     const uint32_t my_tiles = (p.tiles > blockIdx.x) ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (STAGED) {
@@ -293,10 +307,10 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
                     mbar_wait(sbase + 8 * (p.nstages + slot), par);
                     const uint32_t full = sbase + 8 * slot;
                     mbar_arrive_expect_tx(full, stage_bytes);
-                    const uint32_t dst = sbase + kBarBytes + slot * stage_bytes;
+                    const uint32_t dst = sbase + kHdrBytes + slot * stage_bytes;
                     const char* src = src0 + (size_t)q * stage_bytes;
 #pragma unroll
-                    for (int c = 0; c < ILP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
+                    for (int c = 0; c < SP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
                     if (++q == steps) q = 0;
                     if (++slot == p.nstages) { slot = 0; par ^= 1; }
                 }
@@ -306,21 +320,24 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
     }
 
     // ---------------- consumers ----------------
-    const uint32_t col = warp * 32u + lane;
+    const uint32_t grp = warp / P, sub = warp % P;      // tuple group, position inside the warp pair
+    const uint32_t col = grp * 32u + lane;
     const uint32_t xcol = xs_base + col * 4u;
+    const uint32_t xch = sbase + kBarBytes + grp * 256u + lane * 4u;     // + 128 * (step & 1)
     auto feat = [&](uint32_t f) { return lds32(xcol + f * row_bytes); };
     uint32_t slot = 0, par = 0;
 
     for (uint32_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        // ---- load this warp's 32 tuples, transposing row-major global -> feature-major shared ----
+        // ---- load this group's 32 tuples, transposing row-major global -> feature-major shared;
+        //      the P warps of the group take alternate blocks of 16 features ----
         __syncwarp();
         {
             const unsigned long long m = (unsigned long long)tile * M + col;
             const bool live = m < p.n;
             const uint4* row = reinterpret_cast<const uint4*>(p.tuples + (live ? m : 0ull) * p.F);
             const uint32_t nvec = p.F >> 2;
-            uint32_t v = 0;
-            for (; v + 4 <= nvec; v += 4) {
+            uint32_t v = 4 * sub;
+            for (; v + 4 <= nvec; v += 4 * P) {
                 uint4 d0 = ldg128_stream(row + v), d1 = ldg128_stream(row + v + 1);
                 uint4 d2 = ldg128_stream(row + v + 2), d3 = ldg128_stream(row + v + 3);
                 if (!live) { d0 = d1 = d2 = d3 = make_uint4(0, 0, 0, 0); }
@@ -333,14 +350,16 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
                 a += 4 * row_bytes;
                 sts32(a, d3.x); sts32(a + row_bytes, d3.y); sts32(a + 2 * row_bytes, d3.z); sts32(a + 3 * row_bytes, d3.w);
             }
-            for (; v < nvec; ++v) {
-                uint4 d0 = ldg128_stream(row + v);
-                if (!live) d0 = make_uint4(0, 0, 0, 0);
-                uint32_t a = xcol + (4 * v) * row_bytes;
-                sts32(a, d0.x); sts32(a + row_bytes, d0.y); sts32(a + 2 * row_bytes, d0.z); sts32(a + 3 * row_bytes, d0.w);
+            if (sub == 0) {                              // ragged tail (F/4 not a multiple of 4)
+                for (v = nvec & ~3u; v < nvec; ++v) {
+                    uint4 d0 = ldg128_stream(row + v);
+                    if (!live) d0 = make_uint4(0, 0, 0, 0);
+                    uint32_t a = xcol + (4 * v) * row_bytes;
+                    sts32(a, d0.x); sts32(a + row_bytes, d0.y); sts32(a + 2 * row_bytes, d0.z); sts32(a + 3 * row_bytes, d0.w);
+                }
             }
         }
-        __syncwarp();
+        if (P == 2) group_barrier(1 + grp, 64); else __syncwarp();
 
         float acc[8];
 #pragma unroll
@@ -359,6 +378,15 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
                 r = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
                              fadd_ref(fadd_ref(l[4], l[5]), fadd_ref(l[6], l[7])));
                 group_done = true;
+            } else if constexpr (P == 2) {
+                // this warp holds (l0+l1)+(l2+l3) of its four trees; the partner holds the other half of
+                // the tree8 group.  sub 1 hands its half-sum to sub 0 through shared memory.
+                const float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
+                const uint32_t slot_x = xch + 128u * (qf & 1u);
+                if (sub == 1) sts32(slot_x, __float_as_uint(h));
+                group_barrier(1 + grp, 64);
+                r = (sub == 0) ? fadd_ref(h, __uint_as_float(lds32(slot_x))) : 0.0f;
+                group_done = (sub == 0);
             } else {
                 float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
                 group_done = (qf & 1u) != 0;
@@ -366,21 +394,21 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
                 half0 = h;
             }
             if (group_done) {
-                const uint32_t j = (qf / (8 / ILP)) % p.K;
+                const uint32_t j = (qf / (8 / SP)) % p.K;
                 acc_set(acc, j, fadd_ref(r, acc_get(acc, j)));
             }
         };
 
-        // one step, first half: walk the top levels of trees [q*ILP, q*ILP+ILP) and ISSUE the loads of
-        // their bottom records into `dst` (not consumed here)
+        // one step, first half: walk the top levels of this warp's ILP trees of stage q and ISSUE the
+        // loads of their bottom records into `dst` (not consumed here)
         auto walk_top = [&](uint32_t q, BotRec<WIDE> (&dst)[ILP]) {
-            const uint32_t t0 = q * ILP;
+            const uint32_t t0 = q * SP + sub * ILP;
             uint32_t o[ILP];
 #pragma unroll
             for (int c = 0; c < ILP; ++c) o[c] = 0;
             if (STAGED) {
                 mbar_wait(sbase + 8 * slot, par);
-                const uint32_t tb = sbase + kBarBytes + slot * stage_bytes;
+                const uint32_t tb = sbase + kHdrBytes + slot * stage_bytes + sub * ILP * tree_bytes;
                 // Absolute shared-memory addresses: with A = tb_c + o the child address is
                 // A' = tb_c + 2o + 8 + 8*right = (2A + 8 - tb_c) + 8*right.  2A + (8 - tb_c) does not depend
                 // on the feature, so only {compare, select, add} sit between the feature and the next node.
@@ -465,12 +493,14 @@ __global__ void __launch_bounds__(288, 1) dt_walk_tile(const WalkParams p) {
             }
         }
 
-        float tot = 0.0f;
-        for (uint32_t j = 0; j < p.K; ++j) tot = fadd_ref(acc_get(acc, j), tot);
-        const unsigned long long m = (unsigned long long)tile * M + col;
-        if (m < p.n) {
-            p.scores[m] = tot;
-            if (p.labels) p.labels[m] = tot > 0.0f ? 1 : 0;
+        if (sub == 0) {
+            float tot = 0.0f;
+            for (uint32_t j = 0; j < p.K; ++j) tot = fadd_ref(acc_get(acc, j), tot);
+            const unsigned long long m = (unsigned long long)tile * M + col;
+            if (m < p.n) {
+                p.scores[m] = tot;
+                if (p.labels) p.labels[m] = tot > 0.0f ? 1 : 0;
+            }
         }
     }
 }
