@@ -270,8 +270,8 @@ __device__ __forceinline__ void group_barrier(uint32_t id, uint32_t nthreads) {
 }
 
 template <int ILP, int P, bool STAGED, bool WIDE>
-__global__ void __launch_bounds__(ILP == 8 ? 288 : 416, 1) dt_walk_tile(const WalkParams p) {
-    static_assert(P == 1 || (P == 2 && ILP == 4), "a warp pair splits a tree8 group 4 + 4");
+__global__ void __launch_bounds__(ILP == 8 ? 288 : (ILP == 4 ? 416 : 672), 1) dt_walk_tile(const WalkParams p) {
+    static_assert(P == 1 || ILP * P == 8, "P warps split one tree8 group: 4+4 or 2+2+2+2");
     constexpr int BV = WIDE ? 4 : 2;
     constexpr int SP = ILP * P;                         // trees per ring stage / per step
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -323,7 +323,10 @@ __global__ void __launch_bounds__(ILP == 8 ? 288 : 416, 1) dt_walk_tile(const Wa
     const uint32_t grp = warp / P, sub = warp % P;      // tuple group, position inside the warp pair
     const uint32_t col = grp * 32u + lane;
     const uint32_t xcol = xs_base + col * 4u;
-    const uint32_t xch = sbase + kBarBytes + grp * 256u + lane * 4u;     // + 128 * (step & 1)
+    // exchange slots: P=2: 2 x 128 B per group (step parity); P=4: 3 x 128 B per group (sender sub-1).
+    // 6 groups x 256 B or 5 groups x 384 B both stay inside kXchBytes.
+    static_assert(6 * 256 <= kXchBytes && 5 * 384 <= kXchBytes, "exchange area too small");
+    const uint32_t xch = sbase + kBarBytes + grp * (P == 4 ? 384u : 256u) + lane * 4u;
     auto feat = [&](uint32_t f) { return lds32(xcol + f * row_bytes); };
     uint32_t slot = 0, par = 0;
 
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 288 : 416, 1) dt_walk_tile(const Wa
                 }
             }
         }
-        if (P == 2) group_barrier(1 + grp, 64); else __syncwarp();
+        if (P > 1) group_barrier(1 + grp, 32 * P); else __syncwarp();
 
         float acc[8];
 #pragma unroll
@@ -386,6 +389,20 @@ __global__ void __launch_bounds__(ILP == 8 ? 288 : 416, 1) dt_walk_tile(const Wa
                 if (sub == 1) sts32(slot_x, __float_as_uint(h));
                 group_barrier(1 + grp, 64);
                 r = (sub == 0) ? fadd_ref(h, __uint_as_float(lds32(slot_x))) : 0.0f;
+                group_done = (sub == 0);
+            } else if constexpr (P == 4) {
+                // four warps, two trees each: s_sub = l0 + l1; owner forms ((s0+s1)+(s2+s3))
+                const float h = fadd_ref(l[0], l[1]);
+                if (sub != 0) sts32(xch + 128u * (sub - 1u), __float_as_uint(h));
+                group_barrier(1 + grp, 128);
+                if (sub == 0) {
+                    const float s1 = __uint_as_float(lds32(xch)), s2 = __uint_as_float(lds32(xch + 128u));
+                    const float s3 = __uint_as_float(lds32(xch + 256u));
+                    r = fadd_ref(fadd_ref(h, s1), fadd_ref(s2, s3));
+                } else {
+                    r = 0.0f;
+                }
+                group_barrier(1 + grp, 128);             // single exchange buffer: readers done before the next write
                 group_done = (sub == 0);
             } else {
                 float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));

@@ -417,3 +417,18 @@ def test_deeper_than_rtl_limit():
     W, FI = L.synth_ensemble(T, D, F, seed=13)
     x = L.synth_tuples(0, 300, F, seed=14)
     check_case(W, FI, x, D, 1, 1)
+
+
+@pytest.mark.parametrize("tune", ["pair=1,ilp=8,stages=1", "pair=1,ilp=4,stages=2", "pair=2,stages=1", "pair=2,stages=2",
+                                  "pair=4,stages=1", "pair=1,ilp=8,stages=2,warps=3", "pair=2,stages=1,warps=4"])
+def test_every_launch_plan_is_bit_exact(tune, monkeypatch):
+    """The planner's alternatives (trees per warp x warps per tuple group x ring stages) must all give
+    the oracle's words: DTE_TUNE pins a plan for engines created while it is set."""
+    monkeypatch.setenv("DTE_TUNE", tune)
+    T, D, F, K, S, n = 72, 9, 64, 4, 3, 1500          # T % 8 == 0 but 3 slots x 4 clusters x 8 = 96 > T: empty groups
+    W, FI = L.synth_ensemble(T, D, F, seed=91)
+    x = L.synth_tuples(0, n, F, seed=92, missing_ppm=20000)
+    check_case(W, FI, x, D, K, S, variants=[E.DTE_KERNEL_TILE_STAGED, E.DTE_KERNEL_TILE])
+    W, FI = L.synth_ensemble(16, 12, 256, seed=93)   # the headline geometry, few trees
+    x = L.synth_tuples(0, 700, 256, seed=94)
+    check_case(W, FI, x, 12, 8, 1, variants=[E.DTE_KERNEL_TILE_STAGED])
