@@ -281,7 +281,7 @@ Plan make_plan(const dte_engine* e) {
     auto max_groups = [&](int ilp, int pair, int nstages) -> int {
         const size_t fixed = tile_smem(F, 0, ilp * pair, nstages, e->top_stride);
         if (fixed >= budget) return 0;
-        const int warp_cap = (ilp == 8) ? 8 : (ilp == 4 ? 12 : 20);   // __launch_bounds__ of dt_walk_tile (+1 producer warp)
+        const int warp_cap = (pair == 4) ? 20 : (ilp == 8 ? 8 : 12);   // __launch_bounds__ of dt_walk_tile (+1 producer warp)
         int g = (int)std::min<size_t>((size_t)(warp_cap / pair), (budget - fixed) / ((size_t)F * 128));
         if (e->tune.warps) g = std::min(g, std::max(1, e->tune.warps / pair));
         return g;
@@ -298,7 +298,7 @@ Plan make_plan(const dte_engine* e) {
             int ilp = e->tune.ilp ? e->tune.ilp : c[0];
             int pair = e->tune.pair ? e->tune.pair : c[1];
             int st = e->tune.stages ? e->tune.stages : c[2];
-            if (pair == 4) ilp = 2; else if (pair == 2) ilp = 4; else { pair = 1; if (ilp != 4 && ilp != 8) ilp = 8; }
+            if (pair == 4) ilp = 2; else if (pair == 2) ilp = (ilp == 2) ? 2 : 4; else { pair = 1; if (ilp != 4 && ilp != 8) ilp = 8; }
             st = std::max(1, std::min(st, 8));
             const int g = max_groups(ilp, pair, st);
             const int score = g * pair * ilp * 8 + (pair == 2 ? 4 : 0) - (pair == 4 ? 4 : 0) + st;
@@ -382,6 +382,7 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
         if (staged) {
             if (pl.ilp == 8) rc = DTE_LAUNCH(8, 1, true);
             else if (pl.pair == 4) rc = DTE_LAUNCH(2, 4, true);
+            else if (pl.pair == 2 && pl.ilp == 2) rc = DTE_LAUNCH(2, 2, true);
             else if (pl.pair == 2) rc = DTE_LAUNCH(4, 2, true);
             else rc = DTE_LAUNCH(4, 1, true);
         } else {

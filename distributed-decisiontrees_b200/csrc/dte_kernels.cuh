@@ -270,8 +270,8 @@ __device__ __forceinline__ void group_barrier(uint32_t id, uint32_t nthreads) {
 }
 
 template <int ILP, int P, bool STAGED, bool WIDE>
-__global__ void __launch_bounds__(ILP == 8 ? 288 : (ILP == 4 ? 416 : 672), 1) dt_walk_tile(const WalkParams p) {
-    static_assert(P == 1 || ILP * P == 8, "P warps split one tree8 group: 4+4 or 2+2+2+2");
+__global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_walk_tile(const WalkParams p) {
+    static_assert(ILP * P == 8 || ILP * P == 4, "a step covers a tree8 group or half of one");
     constexpr int BV = WIDE ? 4 : 2;
     constexpr int SP = ILP * P;                         // trees per ring stage / per step
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -375,38 +375,39 @@ __global__ void __launch_bounds__(ILP == 8 ? 288 : (ILP == 4 ? 416 : 672), 1) dt
             float l[ILP];
 #pragma unroll
             for (int c = 0; c < ILP; ++c) l[c] = bot_finish<WIDE>(rec[c], p.missing, feat);
-            float r;
-            bool group_done;
-            if constexpr (ILP == 8) {
-                r = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
+            // (1) this warp's share of the tree8 pairing ((l0+l1)+(l2+l3))+((l4+l5)+(l6+l7))
+            float h;
+            if constexpr (ILP == 8)
+                h = fadd_ref(fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3])),
                              fadd_ref(fadd_ref(l[4], l[5]), fadd_ref(l[6], l[7])));
-                group_done = true;
-            } else if constexpr (P == 2) {
-                // this warp holds (l0+l1)+(l2+l3) of its four trees; the partner holds the other half of
-                // the tree8 group.  sub 1 hands its half-sum to sub 0 through shared memory.
-                const float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
-                const uint32_t slot_x = xch + 128u * (qf & 1u);
+            else if constexpr (ILP == 4)
+                h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
+            else
+                h = fadd_ref(l[0], l[1]);
+            // (2) combine the P warps of the group in pairing order; only sub 0 continues
+            if constexpr (P == 2) {
+                const uint32_t slot_x = xch + 128u * (qf & 1u);              // double-buffered by step parity
                 if (sub == 1) sts32(slot_x, __float_as_uint(h));
                 group_barrier(1 + grp, 64);
-                r = (sub == 0) ? fadd_ref(h, __uint_as_float(lds32(slot_x))) : 0.0f;
-                group_done = (sub == 0);
+                if (sub == 0) h = fadd_ref(h, __uint_as_float(lds32(slot_x)));
             } else if constexpr (P == 4) {
-                // four warps, two trees each: s_sub = l0 + l1; owner forms ((s0+s1)+(s2+s3))
-                const float h = fadd_ref(l[0], l[1]);
                 if (sub != 0) sts32(xch + 128u * (sub - 1u), __float_as_uint(h));
                 group_barrier(1 + grp, 128);
                 if (sub == 0) {
                     const float s1 = __uint_as_float(lds32(xch)), s2 = __uint_as_float(lds32(xch + 128u));
                     const float s3 = __uint_as_float(lds32(xch + 256u));
-                    r = fadd_ref(fadd_ref(h, s1), fadd_ref(s2, s3));
-                } else {
-                    r = 0.0f;
+                    h = fadd_ref(fadd_ref(h, s1), fadd_ref(s2, s3));
                 }
                 group_barrier(1 + grp, 128);             // single exchange buffer: readers done before the next write
+            }
+            // (3) a step covers SP = ILP*P trees: a whole tree8 group, or half of one
+            float r;
+            bool group_done;
+            if constexpr (SP == 8) {
+                r = h;
                 group_done = (sub == 0);
             } else {
-                float h = fadd_ref(fadd_ref(l[0], l[1]), fadd_ref(l[2], l[3]));
-                group_done = (qf & 1u) != 0;
+                group_done = (sub == 0) && (qf & 1u) != 0;
                 r = fadd_ref(half0, h);
                 half0 = h;
             }
