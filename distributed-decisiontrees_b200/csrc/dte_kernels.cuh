@@ -9,13 +9,20 @@
 //
 // B200 mapping (nothing here resembles the FPGA pipeline):
 //   * lane = tuple.  A warp owns 32 tuples and walks the SAME tree in all lanes, so the upper tree
-//     levels are shared-memory / L1 broadcasts and the tuple tile can be stored feature-major
+//     levels are shared-memory broadcasts and the tuple tile can be stored feature-major
 //     (xs[f][column]) which makes every per-lane feature fetch bank-conflict free.
 //   * one lane accumulates all trees of its tuple in the reference's summation order, so scores
-//     are bit-exact with the oracle; ILP comes from walking 4 or 8 trees of a tree8 group at once.
+//     are bit-exact with the oracle.  Two warps serve each 32-tuple group (4 trees each of every
+//     tree8 group, half-sums exchanged through shared memory in pairing order): the tile, not the
+//     warp count, fills the SM, so this doubles the warps per SM for free.
+//   * inside a warp the 4 (8) walks are issued in a skewed order — node load, feature load and
+//     compare of different walks interleave — so an in-order warp always has independent work
+//     between a shared-memory load and its first use.
 //   * the ensemble is repacked on load: levels 0..D-3 as 8-byte heap records ("top"), and the two
 //     last comparison levels plus their four leaves as ONE 32-byte sector-aligned record
-//     ("bottom") — the deep, divergent part of a walk costs one L2 sector instead of three.
+//     ("bottom") fetched with one 256-bit load (LDG.E.256, new on sm_100) — the deep, divergent
+//     part of a walk costs one L2 sector instead of three, and the fetch of step q is consumed
+//     after the top walk of step q+1 (two register buffers).
 //   * TILE_STAGED: a producer warp streams the top parts of the next trees into a shared-memory
 //     ring with cp.async.bulk + mbarrier (TMA bulk copy engine) while the consumer warps walk.
 #pragma once
