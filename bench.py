@@ -352,11 +352,39 @@ def main():
             a.record(); e1.infer_device(d_x, n1, tmp, None, stream=st); b.record(); torch.cuda.synchronize()
             one_ms = a.elapsed_time(b) * (ne / n1)
             e1.close()
+        # the same step with the combine FUSED into the walk epilogue (red.add over NVLink peer memory)
+        fused_ms = None
+        try:
+            fc = ddt.sharding.FusedCombine(ee, dist, ne, dst=0)
+            for _ in range(2):
+                fc.step(d_x, ne, st)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                out = fc.step(d_x, ne, st)
+                if rank == 0:
+                    ee.labels_device(out, ne, d_l, stream=st)
+            torch.cuda.synchronize()
+            tf = torch.tensor([(time.perf_counter() - t0) / 3 * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            fused_ms = float(tf.item())
+            fused_ok = None
+            if rank == 0:
+                estep()                                            # NCCL result into `part` for comparison
+                torch.cuda.synchronize()
+                fused_ok = bool(torch.allclose(out, part, rtol=1e-5, atol=1e-7))
+            else:
+                estep()
+            fc.close()
+        except Exception as ex:                                    # IPC not permitted in this container etc.
+            fused_ms, fused_ok = None, "unavailable: %s" % ex
         ens = {"workload": "cfg4: %d trees split %d/GPU, D=10, 256 features, %d tuples on every GPU, one NCCL reduce(SUM) of fp32[%d] to rank 0"
                            % (Te, count, ne, ne),
                "ms_per_step": float(ms.item()), "tuples_per_s": ne / (float(ms.item()) * 1e-3),
                "one_gpu_all_trees_ms_extrapolated": one_ms,
-               "speedup_vs_one_gpu": (one_ms / float(ms.item())) if one_ms else None}
+               "speedup_vs_one_gpu": (one_ms / float(ms.item())) if one_ms else None,
+               "fused_epilogue": {"what": "combine fused into the walk kernel (system-scope red.add into rank 0's IPC buffer over NVLink), no collective",
+                                  "ms_per_step": fused_ms, "matches_nccl_within_1e-5": fused_ok,
+                                  "speedup_vs_one_gpu": (one_ms / fused_ms) if (one_ms and fused_ms) else None}}
         ee.close()
 
     if rank == 0:

@@ -338,7 +338,8 @@ cudaError_t launch_tile(const WalkParams& wp, int grid, int threads, size_t smem
     return cudaGetLastError();
 }
 
-int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, uint8_t* d_labels, cudaStream_t st) {
+int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, uint8_t* d_labels, cudaStream_t st,
+                bool accumulate = false) {
     if (!e->d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
     if (n == 0) return DTE_OK;
     const Plan pl = make_plan(e);
@@ -359,6 +360,7 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
     wp.missing = e->missing;
     wp.nwarps = (uint32_t)pl.nwarps;
     wp.nstages = (uint32_t)pl.nstages;
+    wp.accumulate = accumulate ? 1u : 0u;
     wp.tiles = 0;
     cudaError_t rc;
     if (pl.variant == DTE_KERNEL_GENERIC) {
@@ -723,6 +725,55 @@ int dte_infer_device(dte_t* e, const void* d_tuples, size_t n, float* d_scores, 
     e->tuples_in += n;
     e->tuples_out += n;
     if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
+    return DTE_OK;
+}
+
+int dte_infer_device_accumulate(dte_t* e, const void* d_tuples, size_t n, float* d_scores_accum, void* cuda_stream) {
+    if (!e || (n && (!d_tuples || !d_scores_accum))) return DTE_ERR_ARG;
+    CUDA_TRY(e, cudaSetDevice(e->dev));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->s_main;
+    CUDA_TRY(e, cudaEventRecord(e->ev_t0, st));
+    int rc = launch_walk(e, d_tuples, n, d_scores_accum, nullptr, st, true);
+    if (rc) return rc;
+    CUDA_TRY(e, cudaEventRecord(e->ev_t1, st));
+    e->timing_pending = true;
+    e->tuples_in += n;
+    e->tuples_out += n;
+    if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
+    return DTE_OK;
+}
+
+// ---- peer-visible buffers (CUDA IPC): the combine target of the fused cross-device reduce ----
+int dte_ipc_alloc(dte_t* e, size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+    if (!e || !d_ptr || !handle_out || !bytes) return DTE_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CUDA_TRY(e, cudaSetDevice(e->dev));
+    CUDA_TRY(e, cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t st = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (st != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return fail(e, DTE_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(st));
+    }
+    memcpy(handle_out, &h, 64);
+    return DTE_OK;
+}
+
+int dte_ipc_open(dte_t* e, const unsigned char handle[64], void** d_ptr) {
+    if (!e || !handle || !d_ptr) return DTE_ERR_ARG;
+    CUDA_TRY(e, cudaSetDevice(e->dev));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(e, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DTE_OK;
+}
+
+int dte_ipc_close(dte_t* e, void* d_ptr, int owner) {
+    if (!e || !d_ptr) return DTE_ERR_ARG;
+    CUDA_TRY(e, cudaSetDevice(e->dev));
+    if (owner) CUDA_TRY(e, cudaFree(d_ptr));
+    else CUDA_TRY(e, cudaIpcCloseMemHandle(d_ptr));
     return DTE_OK;
 }
 

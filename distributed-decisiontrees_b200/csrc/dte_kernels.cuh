@@ -48,6 +48,7 @@ struct WalkParams {
     uint32_t tiles;             // ceil(n / tuples_per_cta)
     uint32_t nwarps;            // consumer warps per CTA (tuples_per_cta = 32 * nwarps)
     uint32_t nstages;           // ring depth (TILE_STAGED)
+    uint32_t accumulate;        // 1: scores[i] += partial with a system-scope reduction (fused cross-device combine)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -58,6 +59,11 @@ __device__ __forceinline__ float fadd_ref(float a, float b) {
     float r;
     asm("add.rn.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
+}
+// fire-and-forget fp32 add into memory that may belong to a peer GPU (NVLink): the ResultsCombiner
+// hop (ResultsCombiner.sv:292-311) done by the walk kernel's own epilogue instead of a collective
+__device__ __forceinline__ void red_add_sys(float* addr, float v) {
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
@@ -251,8 +257,12 @@ __global__ void __launch_bounds__(128) dt_walk_generic(const WalkParams p) {
     }
     float tot = 0.0f;
     for (uint32_t j = 0; j < p.K; ++j) tot = fadd_ref(acc_get(acc, j), tot);   // Core.sv:486-542
-    p.scores[i] = tot;
-    if (p.labels) p.labels[i] = tot > 0.0f ? 1 : 0;
+    if (p.accumulate) {
+        red_add_sys(p.scores + i, tot);
+    } else {
+        p.scores[i] = tot;
+        if (p.labels) p.labels[i] = tot > 0.0f ? 1 : 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -523,8 +533,12 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
             for (uint32_t j = 0; j < p.K; ++j) tot = fadd_ref(acc_get(acc, j), tot);
             const unsigned long long m = (unsigned long long)tile * M + col;
             if (m < p.n) {
-                p.scores[m] = tot;
-                if (p.labels) p.labels[m] = tot > 0.0f ? 1 : 0;
+                if (p.accumulate) {
+                    red_add_sys(p.scores + m, tot);
+                } else {
+                    p.scores[m] = tot;
+                    if (p.labels) p.labels[m] = tot > 0.0f ? 1 : 0;
+                }
             }
         }
     }

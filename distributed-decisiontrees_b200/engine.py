@@ -31,6 +31,10 @@ ABI = [
     ("dte_load_ensemble", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
     ("dte_infer_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dte_infer_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("dte_infer_device_accumulate", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    ("dte_ipc_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    ("dte_ipc_open", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("dte_ipc_close", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("dte_labels_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     ("dte_ring_add_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("dte_csr_from_profile", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _u64p]),
@@ -210,6 +214,26 @@ class Engine:
         labels = out_labels if out_labels is not None else (np.empty(n, dtype=np.uint8) if want_labels else None)
         self._check(self._lib.dte_infer_host(self._h, _ptr(t), n, _ptr(scores), _ptr(labels)))
         return scores, labels
+
+    def infer_device_accumulate(self, d_tuples, n, d_scores_accum, stream=None):
+        """Walk and ADD the partial scores into d_scores_accum (local or peer-GPU buffer), fused in the kernel."""
+        self._check(self._lib.dte_infer_device_accumulate(self._h, _ptr(d_tuples), int(n), _ptr(d_scores_accum),
+                                                          _ptr(stream) if stream else None))
+
+    def ipc_alloc(self, nbytes):
+        """-> (device pointer, 64-byte handle) of a buffer other processes can open."""
+        ptr = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.dte_ipc_alloc(self._h, int(nbytes), C.byref(ptr), buf))
+        return int(ptr.value), bytes(buf.raw)
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        self._check(self._lib.dte_ipc_open(self._h, C.c_char_p(bytes(handle)), C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr, owner):
+        self._check(self._lib.dte_ipc_close(self._h, C.c_void_p(int(ptr)), 1 if owner else 0))
 
     def labels_device(self, d_scores, n, d_labels, stream=None):
         self._check(self._lib.dte_labels_device(self._h, _ptr(d_scores), int(n), _ptr(d_labels),

@@ -75,3 +75,74 @@ def deal_batches(n_lines, batch_cls, world):
         pos += take
         dev = (dev + 1) % world
     return out
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can view a raw device pointer (zero copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(n),), "typestr": "<f4", "version": 2}
+
+
+class FusedCombine:
+    """Ensemble-sharded combine fused into the walk kernel.
+
+    Rank `dst` owns a peer-visible fp32[n] buffer (CUDA IPC through libdte.so); every rank's walk
+    kernel adds its partial scores straight into it over NVLink (`red.relaxed.sys.global.add.f32` in
+    the epilogue) — no separate reduce kernel, no collective on the data path.  torch.distributed is
+    used only to hand the 64-byte handle around and for the two host barriers of a step."""
+
+    def __init__(self, engine, dist, n, dst=0):
+        import torch
+        self.engine, self.dist, self.n, self.dst = engine, dist, int(n), dst
+        multi = dist is not None and dist.get_world_size() > 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.owner = self.rank == dst
+        self.ptr = None
+        # every rank takes the same decision (no rank may be left waiting in a collective)
+        box = [None]
+        if self.owner:
+            try:
+                self.ptr, handle = engine.ipc_alloc(4 * self.n)
+                box[0] = handle
+            except Exception as ex:                      # noqa: BLE001
+                box[0] = "error: %s" % ex
+        if multi:
+            dist.broadcast_object_list(box, src=dst)
+        err = box[0] if isinstance(box[0], str) else None
+        if err is None and not self.owner:
+            try:
+                self.ptr = engine.ipc_open(box[0])
+            except Exception as ex:                      # noqa: BLE001
+                err = "error: %s" % ex
+        if multi:
+            flags = [None] * dist.get_world_size()
+            dist.all_gather_object(flags, err)
+            err = next((f for f in flags if f), None)
+        if err:
+            if self.ptr is not None:
+                try:
+                    engine.ipc_close(self.ptr, self.owner)
+                except Exception:                        # noqa: BLE001
+                    pass
+                self.ptr = None
+            raise RuntimeError("fused combine unavailable (%s)" % err)
+        self.view = torch.as_tensor(_CudaArray(self.ptr, self.n), device="cuda") if self.owner else None
+
+    def step(self, d_tuples, n, stream):
+        """One combined inference: returns the summed scores (torch view) on dst, None elsewhere."""
+        import torch
+        if self.owner:
+            self.view[:n].zero_()
+        torch.cuda.synchronize()
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.barrier()
+        self.engine.infer_device_accumulate(d_tuples, n, self.ptr, stream=stream)
+        torch.cuda.synchronize()
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.barrier()
+        return self.view[:n] if self.owner else None
+
+    def close(self):
+        self.view = None
+        self.engine.ipc_close(self.ptr, self.owner)

@@ -96,6 +96,20 @@ int dte_load_ensemble(dte_t* engine, const void* weight_cls, size_t n_weight_cls
 int dte_infer_device(dte_t* engine, const void* d_tuples, size_t n, float* d_scores,
                      uint8_t* d_labels, void* cuda_stream);
 
+/* Fused cross-device combine (the "next" row N3 of SURVEY.md 8f): walk n tuples and ADD this
+ * device's partial scores into d_scores_accum with a system-scope fp32 reduction issued by the walk
+ * kernel's own epilogue — d_scores_accum may be a buffer of a PEER GPU (opened with dte_ipc_open),
+ * so the ResultsCombiner hop (ResultsCombiner.sv:292-311) rides NVLink with no separate collective.
+ * The target must be zeroed before the first contributor starts; the order of the adds is not the
+ * ring order, so scores agree with the ring to ~1 ulp per device (north_star's 1e-5), not bit-exactly. */
+int dte_infer_device_accumulate(dte_t* engine, const void* d_tuples, size_t n, float* d_scores_accum, void* cuda_stream);
+
+/* Peer-visible device buffers for the call above (cudaIpc*): the owner allocates and publishes the
+ * 64-byte handle by any host channel; the other processes open it.  owner=1 frees, owner=0 unmaps. */
+int dte_ipc_alloc(dte_t* engine, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int dte_ipc_open(dte_t* engine, const unsigned char handle[64], void** d_ptr);
+int dte_ipc_close(dte_t* engine, void* d_ptr, int owner);
+
 /* Same from host memory: chunks, overlaps H2D / walk / D2H on the engine's streams, returns when
  * h_scores (and h_labels if not NULL) are complete.  Pinned host buffers give full PCIe speed. */
 int dte_infer_host(dte_t* engine, const void* h_tuples, size_t n, float* h_scores, uint8_t* h_labels);

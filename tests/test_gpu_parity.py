@@ -433,3 +433,38 @@ def test_every_launch_plan_is_bit_exact(tune, monkeypatch):
     W, FI = L.synth_ensemble(16, 12, 256, seed=93)   # the headline geometry, few trees
     x = L.synth_tuples(0, 700, 256, seed=94)
     check_case(W, FI, x, 12, 8, 1, variants=[E.DTE_KERNEL_TILE_STAGED])
+
+
+def test_fused_accumulate_epilogue(torch_cuda):
+    """N3: the walk kernel adds its partial scores into a shared target with a system-scope reduction
+    (dte_infer_device_accumulate).  Two contributors: a+b is commutative -> bit-exact with the ring;
+    three contributors: the order is free -> 1e-5 relative (north_star tolerance), labels stable."""
+    torch = torch_cuda
+    T, D, F, K, n = 96, 7, 64, 2, 6000
+    W, FI = L.synth_ensemble(T, D, F, seed=51)
+    x = L.synth_tuples(0, n, F, seed=52)
+    wl, fl = L.pack_streams(W, FI, D)
+    dx = torch.from_numpy(x.view(np.int32)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for ndev in (2, 3):
+        target = torch.zeros(n, dtype=torch.float32, device="cuda")
+        parts, engines = [], []
+        for g in range(ndev):
+            first, count = ddt.sharding.ensemble_chunk(T, g, ndev)
+            Kd, Sd = ddt.sharding.shard_geometry(T, D, K, ndev)
+            e = make_engine(T, D, F, Kd, Sd)
+            e.load_ensemble(wl, fl, first_tree=first, num_local_trees=count)
+            e.infer_device_accumulate(dx, n, target, stream=st)
+            engines.append(e)
+            cw, cf = L.pack_streams(W[first:first + count], FI[first:first + count], D)
+            parts.append(O.scores(oracle_cfg(D, Kd, Sd, L.MISSING_DEFAULT, F, count), cw, cf, x, threads=8))
+        torch.cuda.synchronize()
+        want = O.ring_combine(parts)
+        got = target.cpu().numpy()
+        if ndev == 2:
+            assert (got.view(np.uint32) == want).all()
+        else:
+            assert np.allclose(got, want.view(np.float32), rtol=1e-5, atol=1e-7)
+        assert (O.labels(got.view(np.uint32)) == O.labels(want)).mean() > 0.999
+        for e in engines:
+            e.close()
