@@ -161,8 +161,17 @@ def run_reference(args):
                 "this arm is the RTL-faithful oracle port on all host cores",
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)            # libraries that print to fd 1 (e.g. "NCCL version ...") now land on stderr
 
 
 def main():
@@ -193,7 +202,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device; the engine has no CPU fallback"}))
+        emit({"error": "no CUDA device; the engine has no CPU fallback"})
         return 1
     torch.cuda.set_device(local)
     dist = None
@@ -442,7 +451,7 @@ def main():
         }
         if ens:
             line["ensemble_sharded"] = ens
-        print(json.dumps(line), flush=True)
+        emit(line)
     e.close()
     if dist is not None:
         dist.destroy_process_group()
