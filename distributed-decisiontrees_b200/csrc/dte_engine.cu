@@ -28,7 +28,7 @@ namespace {
 constexpr int kNumBuf = 3;   // device chunk buffers of the host-path pipeline
 
 struct Tune {               // experiment knobs, env DTE_TUNE="ilp=4,pair=2,stages=1,warps=10,chunk=65536"
-    int ilp = 0, stages = 0, warps = 0, pair = 0;
+    int ilp = 0, stages = 0, warps = 0, pair = 0, fill = 0;
     size_t chunk = 0;
 };
 
@@ -131,6 +131,7 @@ void parse_tune(Tune& t) {
             else if (k == "stages") t.stages = (int)v;
             else if (k == "warps") t.warps = (int)v;
             else if (k == "pair") t.pair = (int)v;
+            else if (k == "fill") t.fill = (int)v;
             else if (k == "chunk") t.chunk = (size_t)v;
         }
         if (comma == std::string::npos) break;
@@ -361,6 +362,7 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
     wp.nwarps = (uint32_t)pl.nwarps;
     wp.nstages = (uint32_t)pl.nstages;
     wp.accumulate = accumulate ? 1u : 0u;
+    wp.fill_split = e->tune.fill ? 1u : 0u;      // DTE_TUNE fill=1: one bulk copy per tree instead of one per stage
     wp.tiles = 0;
     cudaError_t rc;
     if (pl.variant == DTE_KERNEL_GENERIC) {

@@ -48,6 +48,7 @@ struct WalkParams {
     uint32_t tiles;             // ceil(n / tuples_per_cta)
     uint32_t nwarps;            // consumer warps per CTA (tuples_per_cta = 32 * nwarps)
     uint32_t nstages;           // ring depth (TILE_STAGED)
+    uint32_t fill_split;        // 0: one bulk copy per ring stage; 1: one per tree
     uint32_t accumulate;        // 1: scores[i] += partial with a system-scope reduction (fused cross-device combine)
 };
 
@@ -91,6 +92,11 @@ __device__ __forceinline__ uint4 ldg128_nc(const void* p) {
 // 256-bit load (sm_100+: LDG.E.256): one instruction, one sector per lane for the bottom records
 __device__ __forceinline__ void ldg256_nc(const void* p, uint4& lo, uint4& hi) {
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256_nc_na(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
 }
@@ -179,7 +185,16 @@ __device__ __forceinline__ void acc_set(float (&a)[8], uint32_t j, float v) {
 template <bool WIDE> struct BotRec;
 template <> struct BotRec<false> { uint4 a, b; };
 template <> struct BotRec<true> { uint4 a, b, c; };
-__device__ __forceinline__ void bot_load(BotRec<false>& r, const uint4* rec) { ldg256_nc(rec, r.a, r.b); }
+#ifndef DTE_BOT_NA
+#define DTE_BOT_NA 1     // bottom records are touched once per (tuple, tree): do not allocate them in L1
+#endif
+__device__ __forceinline__ void bot_load(BotRec<false>& r, const uint4* rec) {
+#if DTE_BOT_NA
+    ldg256_nc_na(rec, r.a, r.b);
+#else
+    ldg256_nc(rec, r.a, r.b);
+#endif
+}
 __device__ __forceinline__ void bot_load(BotRec<true>& r, const uint4* rec) {
     ldg256_nc(rec, r.a, r.b);
     r.c = ldg128_nc(rec + 2);
@@ -326,8 +341,12 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
                     mbar_arrive_expect_tx(full, stage_bytes);
                     const uint32_t dst = sbase + kHdrBytes + slot * stage_bytes;
                     const char* src = src0 + (size_t)q * stage_bytes;
+                    if (p.fill_split == 0) {
+                        bulk_g2s(dst, src, stage_bytes, full);                 // the SP tree tops are contiguous: one copy
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < SP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
+                        for (int c = 0; c < SP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
+                    }
                     if (++q == steps) q = 0;
                     if (++slot == p.nstages) { slot = 0; par ^= 1; }
                 }
