@@ -67,6 +67,7 @@ struct dte_engine {
     std::vector<float> result_words;            // scores not yet returned, tuple order
     size_t result_read_pos = 0;                 // words already handed out
     uint64_t result_lines_out = 0;              // lines produced since start (for process_done)
+    uint32_t out_cl_count = 0;                  // pcie_out_cl_count (DTInference.sv:632-646)
 
     // ---- resident ensemble ----
     uint32_t T = 0;                   // trees resident
@@ -543,6 +544,7 @@ int dte_softreg_write(dte_t* e, uint32_t addr, uint64_t data) {
     e->result_words.clear();
     e->result_read_pos = 0;
     e->result_lines_out = 0;
+    e->out_cl_count = 0;
     const uint64_t r201 = e->regs[1];
     const bool data_distributed = r201 & 1, host_node = (r201 >> 1) & 1, rx_enabled = (r201 >> 6) & 1;
     e->state = dte_engine::ST_IDLE;
@@ -684,12 +686,21 @@ int dte_stream_write(dte_t* e, const void* cl128, size_t n_lines) {
     return DTE_OK;
 }
 
-int dte_stream_read(dte_t* e, void* cl128, size_t max_lines, size_t* got) {
+int dte_stream_read_packets(dte_t* e, void* cl128, uint8_t* last_flags, size_t max_lines, size_t* got) {
     if (!e || !got || (!cl128 && max_lines)) return DTE_ERR_ARG;
     // 4 consecutive results per line, word j = tuple 4m+j (ResultsCombiner.sv:132-162)
     const size_t avail_lines = (e->result_words.size() - e->result_read_pos) / 4;
     const size_t n = std::min(avail_lines, max_lines);
     if (n) memcpy(cl128, e->result_words.data() + e->result_read_pos, n * 16);
+    if (last_flags) {
+        // `last` closes a PCIe packet every pcie_out_packet_numcls lines: reg 206[55:48], compared as the
+        // 8-bit "minus one" copy (EngineCSR.sv:242, DTInference.sv:632-646,659-663)
+        const uint32_t pkt_m1 = (uint32_t)(((e->regs[6] >> 48) & 0xFF) - 1) & 0xFF;
+        for (size_t i = 0; i < n; ++i) {
+            last_flags[i] = e->out_cl_count == pkt_m1;
+            e->out_cl_count = (e->out_cl_count == pkt_m1) ? 0 : ((e->out_cl_count + 1) & 0xFF);
+        }
+    }
     e->result_read_pos += n * 4;
     e->result_lines_out += n;
     *got = n;
@@ -698,6 +709,10 @@ int dte_stream_read(dte_t* e, void* cl128, size_t max_lines, size_t* got) {
         e->result_read_pos = 0;
     }
     return DTE_OK;
+}
+
+int dte_stream_read(dte_t* e, void* cl128, size_t max_lines, size_t* got) {
+    return dte_stream_read_packets(e, cl128, nullptr, max_lines, got);
 }
 
 int dte_process_done(dte_t* e, int* done) {

@@ -27,6 +27,7 @@ ABI = [
     ("dte_softreg_read", C.c_int, [C.c_void_p, C.c_uint32, _u64p]),
     ("dte_stream_write", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("dte_stream_read", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("dte_stream_read_packets", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("dte_process_done", C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     ("dte_load_ensemble", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
     ("dte_infer_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -184,6 +185,14 @@ class Engine:
         got = C.c_size_t()
         self._check(self._lib.dte_stream_read(self._h, _ptr(out), int(max_lines), C.byref(got)))
         return out[: got.value]
+
+    def stream_read_packets(self, max_lines):
+        """-> (result lines [n, 4] fp32, last flags [n] u8): `last` closes a PCIe packet (DTInference.sv:659-663)."""
+        out = np.empty((int(max_lines), 4), dtype=np.float32)
+        last = np.zeros(int(max_lines), dtype=np.uint8)
+        got = C.c_size_t()
+        self._check(self._lib.dte_stream_read_packets(self._h, _ptr(out), _ptr(last), int(max_lines), C.byref(got)))
+        return out[: got.value], last[: got.value]
 
     def process_done(self):
         d = C.c_int()

@@ -76,6 +76,9 @@ int dte_stream_write(dte_t* engine, const void* cl128, size_t n_lines);
  * blocks; *got = lines copied.  A trailing group of fewer than 4 results stays inside the engine
  * exactly as in the RTL (ResultsCombiner.sv:153-155). */
 int dte_stream_read(dte_t* engine, void* cl128, size_t max_lines, size_t* got);
+/* Same, also returning the PCIe packet framing: last_flags[i] = 1 when line i closes a packet of
+ * pcie_out_packet_numcls lines (reg 206[55:48]; `last` of pcie_packet_out, DTInference.sv:659-663). */
+int dte_stream_read_packets(dte_t* engine, void* cl128, uint8_t* last_flags, size_t max_lines, size_t* got);
 /* 1 when as many result lines as reg 207[31:0] asks for have been produced
  * (process_done, rtl/DTEngine/DTInference.sv:633-663). */
 int dte_process_done(dte_t* engine, int* done);

@@ -183,6 +183,14 @@ def test_register_and_line_stream_interface():
         again = e.stream_read(100)
         assert (again.reshape(-1).view(np.uint32) == want[:64].view(np.uint32)).all()
         assert e.softreg_read(223) > 0 and e.softreg_read(125) == T
+        # packet framing of the output stream: `last` every pcie_out_packet_numcls lines (reg 206[55:48] = 8)
+        e.start()
+        e.stream_write(x[:400].view(np.uint8).reshape(-1, 16))
+        lines, last = e.stream_read_packets(37)
+        lines2, last2 = e.stream_read_packets(1000)
+        flags = np.concatenate([last, last2])
+        assert flags.size == 100 and (np.nonzero(flags)[0] == np.arange(7, 100, 8)).all()
+        assert (np.concatenate([lines, lines2]).reshape(-1).view(np.uint32) == want[:400].view(np.uint32)).all()
 
 
 def test_error_paths():
