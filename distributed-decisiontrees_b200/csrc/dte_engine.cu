@@ -28,7 +28,7 @@ namespace {
 constexpr int kNumBuf = 3;   // device chunk buffers of the host-path pipeline
 
 struct Tune {               // experiment knobs, env DTE_TUNE="ilp=4,pair=2,stages=1,warps=10,chunk=65536"
-    int ilp = 0, stages = 0, warps = 0, pair = 0, fill = 0;
+    int ilp = 0, stages = 0, warps = 0, pair = 0, fill = 0, phased = -1;
     size_t chunk = 0;
 };
 
@@ -133,6 +133,7 @@ void parse_tune(Tune& t) {
             else if (k == "warps") t.warps = (int)v;
             else if (k == "pair") t.pair = (int)v;
             else if (k == "fill") t.fill = (int)v;
+            else if (k == "phased") t.phased = (int)v;
             else if (k == "chunk") t.chunk = (size_t)v;
         }
         if (comma == std::string::npos) break;
@@ -301,7 +302,7 @@ Plan make_plan(const dte_engine* e) {
             int pair = e->tune.pair ? e->tune.pair : c[1];
             int st = e->tune.stages ? e->tune.stages : c[2];
             if (pair == 4) ilp = 2; else if (pair == 2) ilp = (ilp == 2) ? 2 : 4; else { pair = 1; if (ilp != 4 && ilp != 8) ilp = 8; }
-            st = std::max(1, std::min(st, 8));
+            st = std::max(1, std::min(st, 4));
             const int g = max_groups(ilp, pair, st);
             const int score = g * pair * ilp * 8 + (pair == 2 ? 4 : 0) - (pair == 4 ? 4 : 0) + st;
             if (g >= 1 && score > best) {
@@ -364,6 +365,11 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
     wp.nstages = (uint32_t)pl.nstages;
     wp.accumulate = accumulate ? 1u : 0u;
     wp.fill_split = e->tune.fill ? 1u : 0u;      // DTE_TUNE fill=1: one bulk copy per tree instead of one per stage
+    // phased refill needs >= 3 staged levels and at most 4 ring stages (16 mbarriers in the header)
+    // Measured (profiles/r01_summary.md): +7 % at D = 12 (64 KiB stage), -4 % at D <= 10 (<= 16 KiB stage, the
+    // refill is already cheap there and the extra barrier hand-offs cost more than they hide).
+    const bool phased = e->tune.phased == 1 || (e->tune.phased == -1 && e->Dtop >= 10);
+    wp.Lw = (phased && e->Dtop >= 3 && pl.nstages <= 4) ? e->Dtop - 3 : 0xFFFFFFFFu;
     wp.tiles = 0;
     cudaError_t rc;
     if (pl.variant == DTE_KERNEL_GENERIC) {

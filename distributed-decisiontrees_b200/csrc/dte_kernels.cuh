@@ -49,6 +49,7 @@ struct WalkParams {
     uint32_t nwarps;            // consumer warps per CTA (tuples_per_cta = 32 * nwarps)
     uint32_t nstages;           // ring depth (TILE_STAGED)
     uint32_t fill_split;        // 0: one bulk copy per ring stage; 1: one per tree
+    uint32_t Lw;                // phased ring refill: level iteration at which part B is needed; 0xFFFFFFFF = off
     uint32_t accumulate;        // 1: scores[i] += partial with a system-scope reduction (fused cross-device combine)
 };
 
@@ -322,8 +323,10 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
     if (STAGED) {
         if (threadIdx.x == 0) {
             for (uint32_t s = 0; s < p.nstages; ++s) {
-                mbar_init(sbase + 8 * s, 1);                        // full: producer's arrive + tx bytes
-                mbar_init(sbase + 8 * (p.nstages + s), p.nwarps);   // empty: one arrive per consumer warp
+                mbar_init(sbase + 8 * s, 1);                        // full (part A): producer's arrive + tx bytes
+                mbar_init(sbase + 8 * (p.nstages + s), p.nwarps);   // empty (part A): one arrive per consumer warp
+                mbar_init(sbase + 8 * (2 * p.nstages + s), 1);      // full, part B  (phased refill only)
+                mbar_init(sbase + 8 * (3 * p.nstages + s), p.nwarps);   // empty, part B
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -335,17 +338,38 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
                 const char* src0 = reinterpret_cast<const char*>(p.top);
                 uint32_t slot = 0, par = 1;                          // fresh barrier: parity-1 wait passes
                 uint32_t q = 0;
+                // Phased refill (p.Lw set): a stage is refilled in two parts with their own barriers.
+                //   part A = the first 8*2^(Lw+1) bytes of every tree top (levels 0..Lw and the first record of
+                //   level Lw+1), part B = the rest (75 % of the bytes).  The consumers hand part A back before
+                //   their last level and part B after it, and need part B only from level iteration Lw on, so
+                //   ONE stage overlaps copy and walk: B of step q+1 streams in under levels 0..Lw of step q+1,
+                //   A of step q+1 under the last level + bottom records + leaf sums of step q.
+                const bool phased = p.Lw != 0xFFFFFFFFu;
+                const uint32_t bytesA = phased ? (16u << p.Lw) : tree_bytes;
+                const uint32_t bytesB = tree_bytes - bytesA;
                 for (uint64_t it = 0; it < total; ++it) {
-                    mbar_wait(sbase + 8 * (p.nstages + slot), par);
-                    const uint32_t full = sbase + 8 * slot;
-                    mbar_arrive_expect_tx(full, stage_bytes);
                     const uint32_t dst = sbase + kHdrBytes + slot * stage_bytes;
                     const char* src = src0 + (size_t)q * stage_bytes;
-                    if (p.fill_split == 0) {
-                        bulk_g2s(dst, src, stage_bytes, full);                 // the SP tree tops are contiguous: one copy
-                    } else {
+                    mbar_wait(sbase + 8 * (p.nstages + slot), par);
+                    const uint32_t full = sbase + 8 * slot;
+                    if (!phased) {
+                        mbar_arrive_expect_tx(full, stage_bytes);
+                        if (p.fill_split == 0) {
+                            bulk_g2s(dst, src, stage_bytes, full);                 // the SP tree tops are contiguous: one copy
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < SP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
+                            for (int c = 0; c < SP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, tree_bytes, full);
+                        }
+                    } else {
+                        mbar_arrive_expect_tx(full, (uint32_t)SP * bytesA);
+#pragma unroll
+                        for (int c = 0; c < SP; ++c) bulk_g2s(dst + c * tree_bytes, src + (size_t)c * tree_bytes, bytesA, full);
+                        mbar_wait(sbase + 8 * (3 * p.nstages + slot), par);
+                        const uint32_t fullB = sbase + 8 * (2 * p.nstages + slot);
+                        mbar_arrive_expect_tx(fullB, (uint32_t)SP * bytesB);
+#pragma unroll
+                        for (int c = 0; c < SP; ++c)
+                            bulk_g2s(dst + c * tree_bytes + bytesA, src + (size_t)c * tree_bytes + bytesA, bytesB, fullB);
                     }
                     if (++q == steps) q = 0;
                     if (++slot == p.nstages) { slot = 0; par ^= 1; }
@@ -490,11 +514,17 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
                 for (int c = 0; c < ILP; ++c) S1(c);                         // level 0 nodes
 #pragma unroll
                 for (int c = 0; c < H; ++c) S2(c);                           // level 0 features, first half
+                const bool phased = p.Lw != 0xFFFFFFFFu;
                 for (uint32_t lvl = 0; lvl + 1 < p.Dtop; ++lvl) {
+                    if (phased && lvl == p.Lw) mbar_wait(sbase + 8 * (2 * p.nstages + slot), par);   // part B landed
 #pragma unroll
                     for (int k = 0; k < H; ++k) { S3(k); S1(k); S2(k + H); }         // S2(k+H) still at level lvl
 #pragma unroll
                     for (int k = H; k < ILP; ++k) { S3(k); S1(k); S2(k - H); }       // S2(k-H) already at level lvl+1
+                }
+                if (phased) {                                                // part A is no longer read: hand it back early
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sbase + 8 * (p.nstages + slot));
                 }
 #pragma unroll
                 for (int k = 0; k < H; ++k) { S3(k); S2(k + H); }            // last staged level: no further node
@@ -503,7 +533,7 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
 #pragma unroll
                 for (int c = 0; c < ILP; ++c) o[c] = A[c] - (tb + c * tree_bytes);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sbase + 8 * (p.nstages + slot));
+                if (lane == 0) mbar_arrive(sbase + 8 * ((phased ? 3 * p.nstages : p.nstages) + slot));
                 if (++slot == p.nstages) { slot = 0; par ^= 1; }
             } else {
                 const char* tp = reinterpret_cast<const char*>(p.top + (size_t)t0 * p.top_stride);

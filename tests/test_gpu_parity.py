@@ -429,7 +429,8 @@ def test_deeper_than_rtl_limit():
 
 @pytest.mark.parametrize("tune", ["pair=1,ilp=8,stages=1", "pair=1,ilp=4,stages=2", "pair=2,stages=1", "pair=2,stages=2",
                                   "pair=4,stages=1", "pair=1,ilp=8,stages=2,warps=3", "pair=2,stages=1,warps=4",
-                                  "pair=2,ilp=2,stages=2"])
+                                  "pair=2,ilp=2,stages=2", "pair=2,stages=1,phased=1", "pair=1,ilp=8,stages=1,phased=1",
+                                  "pair=4,stages=2,phased=1"])
 def test_every_launch_plan_is_bit_exact(tune, monkeypatch):
     """The planner's alternatives (trees per warp x warps per tuple group x ring stages) must all give
     the oracle's words: DTE_TUNE pins a plan for engines created while it is set."""
