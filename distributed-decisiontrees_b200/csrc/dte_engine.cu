@@ -368,8 +368,10 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
     // phased refill needs >= 3 staged levels and at most 4 ring stages (16 mbarriers in the header)
     // Measured (profiles/r01_summary.md): +7 % at D = 12 (64 KiB stage), -4 % at D <= 10 (<= 16 KiB stage, the
     // refill is already cheap there and the extra barrier hand-offs cost more than they hide).
-    const bool phased = e->tune.phased == 1 || (e->tune.phased == -1 && e->Dtop >= 10);
-    wp.Lw = (phased && e->Dtop >= 3 && pl.nstages <= 4) ? e->Dtop - 3 : 0xFFFFFFFFu;
+    const bool phased = e->tune.phased >= 1 || (e->tune.phased == -1 && e->Dtop >= 10);
+    // part A = levels 0..Lw; DTE_TUNE phased=k moves the split k-1 levels further up (smaller part A)
+    const uint32_t up = e->tune.phased > 1 ? (uint32_t)e->tune.phased - 1 : 0;
+    wp.Lw = (phased && e->Dtop >= 3 + up && pl.nstages <= 4) ? e->Dtop - 3 - up : 0xFFFFFFFFu;
     wp.tiles = 0;
     cudaError_t rc;
     if (pl.variant == DTE_KERNEL_GENERIC) {
