@@ -27,7 +27,10 @@ namespace {
 
 constexpr int kNumBuf = 3;   // device chunk buffers of the host-path pipeline
 
-struct Tune {               // experiment knobs, env DTE_TUNE="ilp=4,pair=2,stages=1,warps=10,chunk=65536"
+// experiment knobs, env DTE_TUNE="ilp=4,pair=2,stages=1,warps=10,phased=1,fill=0,chunk=65536"
+// (ilp: trees per warp, pair: warps per tuple group, stages: ring depth, warps: consumer-warp cap,
+//  phased: 0 off / k>=1 on with part A ending k levels earlier, fill=1: one bulk copy per tree, chunk: host-path tuples per chunk)
+struct Tune {
     int ilp = 0, stages = 0, warps = 0, pair = 0, fill = 0, phased = -1;
     size_t chunk = 0;
 };

@@ -25,6 +25,9 @@
 //     after the top walk of step q+1 (two register buffers).
 //   * TILE_STAGED: a producer warp streams the top parts of the next trees into a shared-memory
 //     ring with cp.async.bulk + mbarrier (TMA bulk copy engine) while the consumer warps walk.
+//     A stage is refilled in two parts on separate barriers (levels 0..D-5 | D-4..D-3) that the
+//     consumers hand back at different points of the walk, so ONE 64 KiB stage overlaps copy and
+//     walk like a double buffer ("phased refill", used for deep trees).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(128) dt_walk_generic(const WalkParams p) {
 // P = 2 doubles the warps per SM without costing shared memory — the tile, not the warp count,
 // is what fills the SM — so the hardware scheduler, not a static interleave, hides the
 // shared-memory latency.  Shared memory:
-//   [0,128)                       mbarriers: full[nstages], empty[nstages]
+//   [0,128)                       mbarriers: fullA, emptyA, fullB, emptyB per ring stage (<= 4 stages)
 //   [128, 128+2048)               P = 2: half-sum exchange, [group][step parity][lane] fp32
 //   [kHdrBytes, + ring)           STAGED: nstages x (ILP*P) tree tops (top_stride * 8 B each)
 //   [.., + F * M * 4)             xs[f][M] feature-major tuple tile, M = 32 * G columns
