@@ -139,7 +139,8 @@ def run_reference(args):
     threads = O.max_threads()
     S = T_TREES // (8 * CLUSTERS)
     # size the per-step sample once (~8 s of CPU work), then time K steps after W warm-ups
-    _, n, _, pack = oracle_throughput(T_TREES, DEPTH, FEATS, CLUSTERS, S, 8.0, threads)
+    seconds = float(os.environ.get("DTE_BENCH_REF_SECONDS", "8"))       # CPU work per step (tests shrink it)
+    _, n, _, pack = oracle_throughput(T_TREES, DEPTH, FEATS, CLUSTERS, S, seconds, threads)
     cfg, wl, fl, x, _ = pack
     for _ in range(min(args.warmup, 1)):
         O.scores(cfg, wl, fl, x, threads=threads)
