@@ -417,7 +417,18 @@ def main():
             th = O.max_threads()
             v, ns, dt, _ = oracle_throughput(T, D, F, K, S, 12.0, th)
             v1, ns1, dt1, _ = oracle_throughput(T, D, F, K, S, 4.0, 1)
+            # BASELINE configs[0]: 16 trees, depth 4, 32 features, 10k tuples, ONE host thread, median of 21 runs
+            W1, FI1 = L.synth_ensemble(16, 4, 32)
+            wl1, fl1 = L.pack_streams(W1, FI1, 4)
+            x1 = L.synth_tuples(0, 10000, 32)
+            w1c, f1c = L.tree_cls(4)
+            c1 = O.make_cfg(4, 2, 1, L.MISSING_DEFAULT, w1c, f1c, 8, 16)
+            t_cfg1 = []
+            for _ in range(21):
+                t0 = time.perf_counter(); O.scores(c1, wl1, fl1, x1, threads=1); t_cfg1.append(time.perf_counter() - t0)
+            cfg1_rate = 10000 / float(np.median(t_cfg1))
             cpu = {"value": v, "unit": "tuples/s", "cores": th, "kind": "port",
+                   "cfg1_single_thread": {"value": cfg1_rate, "unit": "tuples/s", "what": "BASELINE configs[0]: 16 trees, D=4, 32 features, 10k tuples, 1 thread, median of 21 runs"},
                    "sample": "%d tuples of the same synthetic set in %.1f s on %d threads (oracle/dte_oracle.c); single thread: %.0f tuples/s on %d tuples"
                              % (ns, dt, th, v1, ns1),
                    "single_thread_value": v1,
