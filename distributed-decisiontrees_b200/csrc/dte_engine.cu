@@ -335,13 +335,22 @@ Plan make_plan(const dte_engine* e) {
     return p;
 }
 
-template <int ILP, int P, bool STAGED, bool WIDE>
-cudaError_t launch_tile(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
-    auto k = dt_walk_tile<ILP, P, STAGED, WIDE>;
+template <int ILP, int P, bool STAGED, bool WIDE, int NT>
+cudaError_t launch_tile_nt(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
+    auto k = dt_walk_tile<ILP, P, STAGED, WIDE, NT>;
     cudaError_t rc = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     k<<<grid, threads, smem, st>>>(wp);
     return cudaGetLastError();
+}
+// thread-bound classes (see dt_walk_tile): <= 12 warps -> the 168-register instantiation, else the wide one
+template <int ILP, int P, bool STAGED, bool WIDE>
+cudaError_t launch_tile(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
+    constexpr int NT_MAX = P == 4 ? 672 : (ILP == 8 ? 288 : 416);
+    if constexpr (NT_MAX > 384) {
+        if (threads <= 384) return launch_tile_nt<ILP, P, STAGED, WIDE, 384>(wp, grid, threads, smem, st);
+    }
+    return launch_tile_nt<ILP, P, STAGED, WIDE, NT_MAX>(wp, grid, threads, smem, st);
 }
 
 int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, uint8_t* d_labels, cudaStream_t st,
@@ -367,6 +376,7 @@ int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, 
     wp.nwarps = (uint32_t)pl.nwarps;
     wp.nstages = (uint32_t)pl.nstages;
     wp.accumulate = accumulate ? 1u : 0u;
+    wp.wide_rows = (wp.F % 8 == 0 && (reinterpret_cast<uintptr_t>(d_tuples) & 31u) == 0) ? 1u : 0u;
     wp.fill_split = e->tune.fill ? 1u : 0u;      // DTE_TUNE fill=1: one bulk copy per tree instead of one per stage
     // phased refill needs >= 3 staged levels and at most 4 ring stages (16 mbarriers in the header)
     // Measured (profiles/r01_summary.md): +7 % at D = 12 (64 KiB stage), -4 % at D <= 10 (<= 16 KiB stage, the
@@ -884,6 +894,24 @@ int dte_get_info(dte_t* e, dte_info* info) {
         Plan pl = make_plan(e);
         info->kernel_variant = (uint32_t)pl.variant;
         info->tuples_per_cta = pl.variant == DTE_KERNEL_GENERIC ? 128u : 32u * (uint32_t)(pl.nwarps / pl.pair);
+    }
+    return DTE_OK;
+}
+
+int dte_kernel_name(dte_t* e, char* buf, size_t len) {
+    if (!e || !buf || !len) return DTE_ERR_ARG;
+    if (!e->d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
+    const Plan pl = make_plan(e);
+    if (pl.variant == DTE_KERNEL_GENERIC) {
+        snprintf(buf, len, "dt_walk_generic<%d>", pl.wide ? 1 : 0);
+    } else {
+        const bool staged = pl.variant == DTE_KERNEL_TILE_STAGED;
+        const int threads = 32 * (pl.nwarps + (staged ? 1 : 0));
+        const int nt_max = pl.pair == 4 ? 672 : (pl.ilp == 8 ? 288 : 416);
+        const int nt = (nt_max > 384 && threads <= 384) ? 384 : nt_max;
+        const bool phased = staged && (e->tune.phased >= 1 || (e->tune.phased == -1 && e->Dtop >= 10)) && e->Dtop >= 3;
+        snprintf(buf, len, "dt_walk_tile<%d, %d, %d, %d, %d> warps=%d stages=%d phased=%d threads=%d smem=%zu",
+                 pl.ilp, pl.pair, staged ? 1 : 0, pl.wide ? 1 : 0, nt, pl.nwarps, pl.nstages, phased ? 1 : 0, threads, pl.smem);
     }
     return DTE_OK;
 }

@@ -54,6 +54,7 @@ struct WalkParams {
     uint32_t fill_split;        // 0: one bulk copy per ring stage; 1: one per tree
     uint32_t Lw;                // phased ring refill: level iteration at which part B is needed; 0xFFFFFFFF = off
     uint32_t accumulate;        // 1: scores[i] += partial with a system-scope reduction (fused cross-device combine)
+    uint32_t wide_rows;         // 1: tuple rows are 32-byte aligned (F % 8 == 0, base aligned): 256-bit tile loads
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -68,6 +69,8 @@ __device__ __forceinline__ float fadd_ref(float a, float b) {
 // fire-and-forget fp32 add into memory that may belong to a peer GPU (NVLink): the ResultsCombiner
 // hop (ResultsCombiner.sv:292-311) done by the walk kernel's own epilogue instead of a collective
 __device__ __forceinline__ void red_add_sys(float* addr, float v) {
+    // fp32 reductions on GLOBAL memory round to nearest even and flush subnormal inputs/results to zero (PTX ISA,
+    // atom/red .add.f32) — the same arithmetic as add.rn.ftz.f32; the instruction takes no .ftz modifier.
     asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -109,6 +112,9 @@ __device__ __forceinline__ uint4 ldg128_stream(const void* p) {   // tuples: rea
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+__device__ __forceinline__ void ldg256_stream(const void* p, uint4& lo, uint4& hi) {   // tuples: one request per 32 B sector
+    ldg256_nc_na(p, lo, hi);
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -305,8 +311,11 @@ __device__ __forceinline__ void group_barrier(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int ILP, int P, bool STAGED, bool WIDE>
-__global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_walk_tile(const WalkParams p) {
+// NT = thread bound of the instantiation.  Registers are allocated per SM sub-partition (16 K each), so the
+// per-thread limit is set by ceil(warps / 4): 9..12 warps -> 168 registers, 13..16 warps -> 128.  The planner
+// picks the 384-thread instantiation whenever the plan fits in 12 warps (cfg3: 5 tuple groups x 2 + producer).
+template <int ILP, int P, bool STAGED, bool WIDE, int NT>
+__global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
     static_assert(ILP * P == 8 || ILP * P == 4, "a step covers a tree8 group or half of one");
     constexpr int BV = WIDE ? 4 : 2;
     constexpr int SP = ILP * P;                         // trees per ring stage / per step
@@ -403,25 +412,33 @@ __global__ void __launch_bounds__(P == 4 ? 672 : (ILP == 8 ? 288 : 416), 1) dt_w
             const uint4* row = reinterpret_cast<const uint4*>(p.tuples + (live ? m : 0ull) * p.F);
             const uint32_t nvec = p.F >> 2;
             uint32_t v = 4 * sub;
-            for (; v + 4 <= nvec; v += 4 * P) {
-                uint4 d0 = ldg128_stream(row + v), d1 = ldg128_stream(row + v + 1);
-                uint4 d2 = ldg128_stream(row + v + 2), d3 = ldg128_stream(row + v + 3);
-                if (!live) { d0 = d1 = d2 = d3 = make_uint4(0, 0, 0, 0); }
-                uint32_t a = xcol + (4 * v) * row_bytes;
-                sts32(a, d0.x); sts32(a + row_bytes, d0.y); sts32(a + 2 * row_bytes, d0.z); sts32(a + 3 * row_bytes, d0.w);
-                a += 4 * row_bytes;
-                sts32(a, d1.x); sts32(a + row_bytes, d1.y); sts32(a + 2 * row_bytes, d1.z); sts32(a + 3 * row_bytes, d1.w);
-                a += 4 * row_bytes;
-                sts32(a, d2.x); sts32(a + row_bytes, d2.y); sts32(a + 2 * row_bytes, d2.z); sts32(a + 3 * row_bytes, d2.w);
-                a += 4 * row_bytes;
-                sts32(a, d3.x); sts32(a + row_bytes, d3.y); sts32(a + 2 * row_bytes, d3.z); sts32(a + 3 * row_bytes, d3.w);
+            auto put4 = [&](uint32_t a, const uint4& d) {
+                sts32(a, d.x); sts32(a + row_bytes, d.y); sts32(a + 2 * row_bytes, d.z); sts32(a + 3 * row_bytes, d.w);
+            };
+            if (p.wide_rows) {
+                // rows are 32-byte aligned: one 256-bit request per sector (LDG.E.256) instead of two 128-bit ones
+                for (; v + 4 <= nvec; v += 4 * P) {
+                    uint4 d0, d1, d2, d3;
+                    ldg256_stream(row + v, d0, d1);
+                    ldg256_stream(row + v + 2, d2, d3);
+                    if (!live) { d0 = d1 = d2 = d3 = make_uint4(0, 0, 0, 0); }
+                    const uint32_t a = xcol + (4 * v) * row_bytes;
+                    put4(a, d0); put4(a + 4 * row_bytes, d1); put4(a + 8 * row_bytes, d2); put4(a + 12 * row_bytes, d3);
+                }
+            } else {
+                for (; v + 4 <= nvec; v += 4 * P) {
+                    uint4 d0 = ldg128_stream(row + v), d1 = ldg128_stream(row + v + 1);
+                    uint4 d2 = ldg128_stream(row + v + 2), d3 = ldg128_stream(row + v + 3);
+                    if (!live) { d0 = d1 = d2 = d3 = make_uint4(0, 0, 0, 0); }
+                    const uint32_t a = xcol + (4 * v) * row_bytes;
+                    put4(a, d0); put4(a + 4 * row_bytes, d1); put4(a + 8 * row_bytes, d2); put4(a + 12 * row_bytes, d3);
+                }
             }
             if (sub == 0) {                              // ragged tail (F/4 not a multiple of 4)
                 for (v = nvec & ~3u; v < nvec; ++v) {
                     uint4 d0 = ldg128_stream(row + v);
                     if (!live) d0 = make_uint4(0, 0, 0, 0);
-                    uint32_t a = xcol + (4 * v) * row_bytes;
-                    sts32(a, d0.x); sts32(a + row_bytes, d0.y); sts32(a + 2 * row_bytes, d0.z); sts32(a + 3 * row_bytes, d0.w);
+                    put4(xcol + (4 * v) * row_bytes, d0);
                 }
             }
         }
@@ -606,6 +623,49 @@ __global__ void labels_kernel(const float* __restrict__ s, uint8_t* __restrict__
 __global__ void ring_add_kernel(const float* a, const float* b, float* out, unsigned long long n) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fadd_ref(a[i], b[i]);       // ResultsCombiner.sv:292-311, one hop
+}
+// ResultsCombiner aggregate mode in ONE kernel (ResultsCombiner.sv:292-311,359-368): the host node injects its
+// partial, every following node of the ring emits local + incoming, so
+//     score = (((p[0] + p[1]) + p[2]) + ...) + p[G-1]          each add = add.rn.ftz.f32
+// p[g] may live on a PEER GPU (mapped through peer access or CUDA IPC): the loads ride NVLink, the sum is
+// formed in ring order in registers, so the result is bit-exact with the reference ring, unlike a library
+// reduction whose order is free.  4 tuples per thread = one 128-bit result line (ResultsCombiner.sv:132-162).
+constexpr int kMaxRing = 20;                 // devices_list has 20 entries (EngineCSR.sv:250-296)
+struct RingParts { const float* p[kMaxRing]; };
+__device__ __forceinline__ uint4 ldg128_peer(const void* p) {   // read-once peer data: do not pollute L1
+    uint4 v;
+    asm volatile("ld.global.relaxed.sys.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) ring_combine_kernel(const RingParts parts, int G, float* __restrict__ out,
+                                                           uint8_t* __restrict__ labels, unsigned long long n) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long nline = n >> 2;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nline; i += stride) {
+        uint4 a = ldg128_peer(reinterpret_cast<const uint4*>(parts.p[0]) + i);
+        float s0 = __uint_as_float(a.x), s1 = __uint_as_float(a.y), s2 = __uint_as_float(a.z), s3 = __uint_as_float(a.w);
+#pragma unroll 4
+        for (int g = 1; g < G; ++g) {
+            const uint4 b = ldg128_peer(reinterpret_cast<const uint4*>(parts.p[g]) + i);
+            s0 = fadd_ref(__uint_as_float(b.x), s0); s1 = fadd_ref(__uint_as_float(b.y), s1);     // local + incoming
+            s2 = fadd_ref(__uint_as_float(b.z), s2); s3 = fadd_ref(__uint_as_float(b.w), s3);
+        }
+        reinterpret_cast<float4*>(out)[i] = make_float4(s0, s1, s2, s3);
+        if (labels) {
+            const uint32_t l = (s0 > 0.0f ? 1u : 0u) | (s1 > 0.0f ? 0x100u : 0u) | (s2 > 0.0f ? 0x10000u : 0u) | (s3 > 0.0f ? 0x1000000u : 0u);
+            reinterpret_cast<uint32_t*>(labels)[i] = l;
+        }
+    }
+    // tuples past the last whole line (n % 4): scalar tail, first thread of the grid
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (unsigned long long i = nline << 2; i < n; ++i) {
+            float s = parts.p[0][i];
+            for (int g = 1; g < G; ++g) s = fadd_ref(parts.p[g][i], s);
+            out[i] = s;
+            if (labels) labels[i] = s > 0.0f ? 1 : 0;
+        }
+    }
 }
 __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long seed, unsigned long long idx) {
     unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;

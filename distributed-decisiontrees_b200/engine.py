@@ -41,6 +41,7 @@ ABI = [
     ("dte_csr_from_profile", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _u64p]),
     ("dte_get_info", C.c_int, [C.c_void_p, C.c_void_p]),
     ("dte_set_kernel_variant", C.c_int, [C.c_void_p, C.c_int]),
+    ("dte_kernel_name", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     ("dte_set_node", C.c_int, [C.c_void_p, C.c_uint32]),
     ("dte_synth_tuples_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
                                            C.c_uint32, C.c_uint32, C.c_void_p]),
@@ -263,6 +264,11 @@ class Engine:
 
     def set_kernel_variant(self, variant):
         self._check(self._lib.dte_set_kernel_variant(self._h, int(variant)))
+
+    def kernel_name(self):
+        buf = C.create_string_buffer(256)
+        self._check(self._lib.dte_kernel_name(self._h, buf, 256))
+        return buf.value.decode()
 
     def info(self):
         i = DteInfo()

@@ -150,6 +150,11 @@ typedef struct {
 } dte_info;
 int dte_get_info(dte_t* engine, dte_info* info);
 
+/* Name and launch shape of the walk kernel the next dte_infer_* call will launch, e.g.
+ * "dt_walk_tile<4, 2, 1, 0, 384> warps=10 stages=1 phased=1 threads=352 smem=231552" (template arguments:
+ * trees per warp, warps per tuple group, staged ring, wide records, thread bound). */
+int dte_kernel_name(dte_t* engine, char* buf, size_t len);
+
 typedef enum {
     DTE_KERNEL_AUTO = 0,
     DTE_KERNEL_GENERIC = 1,    /* one thread per tuple, everything from global memory (any F, any D) */

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-2 GPU evidence (run under gpurun from the repo root):  bash tools/gpu_round2.sh <stage>...
+set -u
+mkdir -p gpurun_out
+for stage in "$@"; do
+case "$stage" in
+  tests)    timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -8 ;;
+  sanitize) bash tools/gpu_sanitize.sh 2>&1 | tee gpurun_out/sanitize_summary.txt ;;
+  bench)    timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_full.json ;;
+  benchq)   timeout 600 python bench.py --tuples 8000000 --steps 5 --warmup 3 --no-cpu --e2e-tuples 1000000 > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; echo "benchq rc=$?"; cut -c1-300 gpurun_out/bench_q.json ;;
+  ref)      timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference rc=$?"; cut -c1-300 gpurun_out/bench_reference.json ;;
+  ncu)      B="--tuples 2000000 --steps 2 --warmup 1 --no-cpu --e2e-tuples 200000"
+            timeout 1200 ncu --set full --clock-control none --import-source on -k regex:dt_walk_tile -s 2 -c 1 -f -o gpurun_out/prof_walk python bench.py $B > gpurun_out/prof_walk.log 2>&1; echo "ncu full rc=$?"
+            timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py $B > gpurun_out/launches_bench.log 2>&1; echo "ncu launches rc=$?" ;;
+  *) echo "unknown stage $stage" ;;
+esac
+done
