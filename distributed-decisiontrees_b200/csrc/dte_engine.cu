@@ -1,100 +1,112 @@
-// dte_engine.cu — host side of libdte.so: the C ABI of include/dte.h, the CSR file, the PCIe line
-// stream framer, the ensemble repacker and the kernel launches.  No torch, no Python: plain CUDA
-// runtime.  There is NO CPU compute path in this file — every score comes from a CUDA kernel.
+// dte_engine.cu — host side of libdte.so: the C ABI of include/dte.h.  One handle = the host node's view of a
+// ring of 1..20 devices: ONE soft-register file, ONE PCIe line stream in, ONE result stream out; behind it the
+// per-device pipelines of dte_device.cuh.  No torch, no Python, no NCCL link dependency (libnccl is dlopen'ed
+// only when DTE_OPT_COMBINE = 1): plain CUDA runtime.  There is NO CPU compute path in this file — every score
+// comes from a CUDA kernel.
 //
 // Reference behaviour mirrored here (paths relative to the reference root):
 //   CSR decode ............... rtl/DTEngine/EngineCSR.sv:113-125,189-306
-//   stream order / counting .. rtl/DTEngine/PCIeReceiver.sv:136-139,205-316
-//   tree / tuple framing ..... rtl/DTEngine/InputDistributor.sv:248-296
-//   result packing ........... rtl/DTEngine/ResultsCombiner.sv:132-162
-//   completion ............... rtl/DTEngine/DTInference.sv:633-663
+//   stream order / dealing ... rtl/DTEngine/PCIeReceiver.sv:136-139,205-316
+//   tree / tuple framing ..... rtl/DTEngine/InputDistributor.sv:248-296, data broadcast :199-204
+//   result packing / combine . rtl/DTEngine/ResultsCombiner.sv:132-162,292-311,359-391
+//   completion / counters .... rtl/DTEngine/DTInference.sv:314-374,633-663
 #include "../../include/dte.h"
-#include "dte_kernels.cuh"
+#include "dte_device.cuh"
 
-#include <algorithm>
 #include <chrono>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
+#include <dlfcn.h>
 #include <new>
-#include <string>
-#include <vector>
 
 using namespace dte;
 
 namespace {
+using Clock = std::chrono::steady_clock;
+inline double ns_since(Clock::time_point t0, Clock::time_point t1) {
+    return std::chrono::duration<double, std::nano>(t1 - t0).count();
+}
 
-constexpr int kNumBuf = 3;   // device chunk buffers of the host-path pipeline
-
-// experiment knobs, env DTE_TUNE="ilp=4,pair=2,stages=1,warps=10,phased=1,fill=0,chunk=65536"
-// (ilp: trees per warp, pair: warps per tuple group, stages: ring depth, warps: consumer-warp cap,
-//  phased: 0 off / k>=1 on with part A ending k levels earlier, fill=1: one bulk copy per tree, chunk: host-path tuples per chunk)
-struct Tune {
-    int ilp = 0, stages = 0, warps = 0, pair = 0, fill = 0, phased = -1;
-    size_t chunk = 0;
+// ---- NCCL through dlopen (only for DTE_OPT_COMBINE = 1; the default combine is our own ring-order kernel) ----
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // a copy the process already has (e.g. torch's)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+        if (!h) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+        Reduce = (decltype(Reduce))dlsym(h, "ncclReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        if (!CommInitAll || !CommDestroy || !GroupStart || !GroupEnd || !Reduce) return false;
+        lib = h;
+        return true;
+    }
 };
-
-struct Plan {               // how the next walk will be launched
-    int variant = DTE_KERNEL_GENERIC;
-    int ilp = 8, pair = 1, nstages = 0, nwarps = 0;   // nwarps = consumer warps = groups * pair
-    bool wide = false;
-    size_t smem = 0;
-};
-
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;        // ncclDataType_t / ncclRedOp_t values of nccl.h
 }  // namespace
 
 struct dte_engine {
-    int dev = 0;
-    int sm_count = 0;
-    int smem_optin = 0;
-    cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    bool timing_pending = false;
+    std::vector<Dev> devs;            // devs[d] = device ID d of devices_list = d-th ordinal given at create
+    int pos2dev[kMaxRing];            // ring position -> index into devs (registers 208-210), decoded at start
+    uint32_t node_index = 0;          // single-device handle: the ring position this engine stands for (dte_set_node)
+    Tune tune;
+    int forced_variant = KERNEL_AUTO;
     std::string err;
 
     // ---- CSR file (EngineCSR.sv) ----
     uint64_t regs[12] = {0};          // 200..211 as written
-    // decoded at `start` / load
-    uint32_t D = 0, K = 0, S = 0, missing = 0, w_cls = 0, f_cls = 0, tuple_cls = 0;
+    Geom g;                           // geometry of the current run (committed by `start` / load on success only)
+
+    // ---- options ----
+    uint32_t cycle_mhz = 0;
+    int combine_nccl = 0;
+    size_t opt_queue_lines = 0, opt_chunk_tuples = 0;
 
     // ---- stream state (PCIeReceiver.sv FSM) ----
     enum { ST_IDLE = 0, ST_TREES = 1, ST_WAIT = 2, ST_DATA = 3 } state = ST_IDLE;
     uint64_t lines_received = 0;
-    uint32_t node_index = 0;                    // position in devices_list; 0 = host node (PCIeReceiver.sv:160-178)
     uint64_t cur_w = 0, cur_f = 0, cur_d = 0;   // currWCount / currFCount / currDCount
     uint32_t cur_dev = 0;                       // currDevID
-    uint64_t local_w_lines = 0;                 // weight lines kept by this node
-    std::vector<unsigned char> tree_lines;      // weights then findexes kept by this node, as received
-    std::vector<unsigned char> tuple_partial;   // bytes of an incomplete tuple
-    std::vector<float> result_words;            // scores not yet returned, tuple order
-    size_t result_read_pos = 0;                 // words already handed out
-    uint64_t result_lines_out = 0;              // lines produced since start (for process_done)
-    uint32_t out_cl_count = 0;                  // pcie_out_cl_count (DTInference.sv:632-646)
+    std::vector<std::vector<unsigned char>> tree_w, tree_f;   // tree lines kept per ring position (weights | indexes)
 
-    // ---- resident ensemble ----
-    uint32_t T = 0;                   // trees resident
-    uint32_t Tpad = 0;                // padded to a multiple of 8
-    uint32_t Dtop = 0, top_stride = 1, nb = 1;
-    bool wide = false;
-    uint2* d_top = nullptr;
-    uint4* d_bottom = nullptr;
-    uint64_t ensemble_bytes = 0;
+    // ---- partition of the current run (decided at `start` / load) ----
+    uint32_t ndev_ring = 1;           // numDevs (reg 203[39:32])
+    bool group = false;               // ensemble-sharded lock-step group: data broadcast, partial scores ring-combined
+    bool deal = false;                // data lines dealt round-robin in batches of deal_lines
+    uint64_t deal_lines = 0;
 
-    // ---- host-path device buffers ----
-    void* d_tup[kNumBuf] = {nullptr, nullptr, nullptr};
-    float* d_sc[kNumBuf] = {nullptr, nullptr, nullptr};
-    uint8_t* d_lb[kNumBuf] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_h2d[kNumBuf], ev_comp[kNumBuf], ev_d2h[kNumBuf];
-    size_t chunk_cap = 0;             // tuples per buffer
-    uint32_t chunk_F = 0;
+    // ---- data / result accounting since `start` ----
+    uint64_t data_lines_in = 0;       // data lines received
+    uint64_t res_read = 0;            // results handed out (tuples, in the order this handle exposes them)
+    uint64_t result_lines_out = 0;    // result lines handed out (process_done)
+    uint32_t out_cl_count = 0;        // pcie_out_cl_count (DTInference.sv:632-646)
+    uint64_t ring_cap = 0;            // result queue capacity in tuples
+    uint64_t prog_lines_local = 0, sl3_lines_sent = 0, sl3_res_lines = 0;
+    bool done_latched = false;
 
-    // ---- counters ----
-    int forced_variant = DTE_KERNEL_AUTO;
-    Tune tune;
-    uint64_t kernel_launches = 0;
-    double prog_ns = 0, exec_ns = 0, last_walk_ms = 0;
+    // ---- cumulative counters (cluster counters are only cleared by a hardware reset, DTPUCluster.sv:85-97) ----
+    uint64_t cum_c0 = 0, cum_c0_lines = 0;
     uint64_t tuples_in = 0, tuples_out = 0;
+
+    // ---- timing: progCycles / execCycles (DTInference.sv:330-357) ----
+    Clock::time_point t_start, t_prog0, t_prog1, t_done;
+    bool running = false, prog_seen = false, prog_open = false;
+    double last_walk_ms = 0;
+
+    // ---- NCCL (optional combine) ----
+    NcclApi nccl;
+    std::vector<void*> nccl_comms;
+
+    bool multi() const { return devs.size() > 1; }
 };
 
 namespace {
@@ -118,369 +130,700 @@ int fail(dte_engine* e, int code, const char* fmt, ...) {
             return fail((e), DTE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
                         __FILE__, __LINE__);                                                    \
     } while (0)
+#define TRY(call)                  \
+    do {                           \
+        int _rc = (call);          \
+        if (_rc) return _rc;       \
+    } while (0)
 
-void parse_tune(Tune& t) {
-    const char* s = getenv("DTE_TUNE");
-    if (!s) return;
-    std::string str(s);
-    size_t pos = 0;
-    while (pos < str.size()) {
-        size_t comma = str.find(',', pos);
-        std::string kv = str.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
-        size_t eq = kv.find('=');
-        if (eq != std::string::npos) {
-            std::string k = kv.substr(0, eq);
-            long long v = atoll(kv.c_str() + eq + 1);
-            if (k == "ilp") t.ilp = (int)v;
-            else if (k == "stages") t.stages = (int)v;
-            else if (k == "warps") t.warps = (int)v;
-            else if (k == "pair") t.pair = (int)v;
-            else if (k == "fill") t.fill = (int)v;
-            else if (k == "phased") t.phased = (int)v;
-            else if (k == "chunk") t.chunk = (size_t)v;
-        }
-        if (comma == std::string::npos) break;
-        pos = comma + 1;
-    }
-}
-
-// Decode the geometry registers (EngineCSR.sv:218-233) and check them.
-int decode_csr(dte_engine* e) {
+// Decode the geometry registers (EngineCSR.sv:218-233) into `g` and check them; the engine is not touched.
+int decode_geom(dte_engine* e, Geom& g) {
     const uint64_t r204 = e->regs[4], r205 = e->regs[5];
-    e->w_cls = (uint32_t)((r204 >> 16) & 0xFFFF);
-    e->f_cls = (uint32_t)((r204 >> 32) & 0xFFFF);
-    e->tuple_cls = (uint32_t)((r204 >> 48) & 0xFFFF);
-    e->missing = (uint32_t)(r205 & 0xFFFFFFFFu);
-    e->D = (uint32_t)((r205 >> 32) & 0xF);
-    e->S = (uint32_t)((r205 >> 36) & 0xFF);
-    e->K = (uint32_t)((r205 >> 44) & 0xF);
-    if (e->D < 1) return fail(e, DTE_ERR_CONFIG, "reg 205: num_levels_per_tree = 0");
-    if (e->K < 1 || e->K > 8) return fail(e, DTE_ERR_CONFIG, "reg 205: num_clusters_per_tuple = %u, need 1..8", e->K);
-    if (e->S < 1) return fail(e, DTE_ERR_CONFIG, "reg 205: num_trees_per_pu = 0");
-    if (e->tuple_cls < 1 || e->tuple_cls > 512) return fail(e, DTE_ERR_CONFIG, "reg 204: tuple_numcls = %u, need 1..512", e->tuple_cls);
-    if ((uint64_t)e->w_cls * 4 < (2ull << e->D) - 1)
-        return fail(e, DTE_ERR_CONFIG, "reg 204: tree_weights_numcls = %u too small for %u levels", e->w_cls, e->D);
-    if ((uint64_t)e->f_cls * 8 < (1ull << e->D) - 1)
-        return fail(e, DTE_ERR_CONFIG, "reg 204: tree_feature_index_numcls = %u too small for %u levels", e->f_cls, e->D);
+    g.w_cls = (uint32_t)((r204 >> 16) & 0xFFFF);
+    g.f_cls = (uint32_t)((r204 >> 32) & 0xFFFF);
+    g.tuple_cls = (uint32_t)((r204 >> 48) & 0xFFFF);
+    g.missing = (uint32_t)(r205 & 0xFFFFFFFFu);
+    g.D = (uint32_t)((r205 >> 32) & 0xF);
+    g.S = (uint32_t)((r205 >> 36) & 0xFF);
+    g.K = (uint32_t)((r205 >> 44) & 0xF);
+    if (g.D < 1) return fail(e, DTE_ERR_CONFIG, "reg 205: num_levels_per_tree = 0");
+    if (g.K < 1 || g.K > 8) return fail(e, DTE_ERR_CONFIG, "reg 205: num_clusters_per_tuple = %u, need 1..8", g.K);
+    if (g.S < 1) return fail(e, DTE_ERR_CONFIG, "reg 205: num_trees_per_pu = 0");
+    if (g.tuple_cls < 1 || g.tuple_cls > 512) return fail(e, DTE_ERR_CONFIG, "reg 204: tuple_numcls = %u, need 1..512", g.tuple_cls);
+    if ((uint64_t)g.w_cls * 4 < (2ull << g.D) - 1)
+        return fail(e, DTE_ERR_CONFIG, "reg 204: tree_weights_numcls = %u too small for %u levels", g.w_cls, g.D);
+    if ((uint64_t)g.f_cls * 8 < (1ull << g.D) - 1)
+        return fail(e, DTE_ERR_CONFIG, "reg 204: tree_feature_index_numcls = %u too small for %u levels", g.f_cls, g.D);
     return DTE_OK;
 }
 
-void free_ensemble(dte_engine* e) {
-    if (e->d_top) cudaFree(e->d_top);
-    if (e->d_bottom) cudaFree(e->d_bottom);
-    e->d_top = nullptr;
-    e->d_bottom = nullptr;
-    e->T = e->Tpad = 0;
-    e->ensemble_bytes = 0;
+// A run may reuse the resident ensemble only with the geometry it was loaded with (F and D fix the device
+// layout and the validated feature-index range; K, S and the missing pattern are free to change).
+int check_resident(dte_engine* e, const Geom& g) {
+    for (Dev& d : e->devs) {
+        if (!d.d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
+        if (d.g.tuple_cls != g.tuple_cls || d.g.D != g.D)
+            return fail(e, DTE_ERR_CONFIG, "registers describe %u features / %u levels but the resident ensemble was loaded with %u / %u",
+                        g.F(), g.D, d.g.F(), d.g.D);
+    }
+    return DTE_OK;
 }
 
-// Repack trees [first, first+count) of the two reference streams into the device layout and upload.
-//   stream layout (R1 in SURVEY.md): per tree, W = heap array of 2^(D+1)-1 fp32 words padded to
-//   w_cls lines; FI = 2^D-1 u16 padded to f_cls lines (DTPU.sv:282-338,579-596).
-int load_ensemble(dte_engine* e, const unsigned char* wl, size_t n_wl, const unsigned char* fl, size_t n_fl,
-                  uint32_t first, uint32_t count) {
-    auto t_begin = std::chrono::steady_clock::now();
-    int rc = decode_csr(e);
-    if (rc) return rc;
-    if (n_wl % e->w_cls) return fail(e, DTE_ERR_ARG, "weights stream: %zu lines is not a multiple of %u lines per tree", n_wl, e->w_cls);
-    const size_t T_all = n_wl / e->w_cls;
-    if (n_fl != T_all * e->f_cls)
-        return fail(e, DTE_ERR_ARG, "feature-index stream: %zu lines, expected %zu (= %zu trees x %u)", n_fl, T_all * e->f_cls, T_all, e->f_cls);
-    if (count == 0 && first == 0) count = (uint32_t)T_all;
-    if ((size_t)first + count > T_all || count == 0)
-        return fail(e, DTE_ERR_ARG, "tree chunk [%u, %u) outside the %zu trees of the stream", first, first + count, T_all);
+void free_ensemble(Dev& d) {
+    cudaSetDevice(d.ordinal);
+    if (d.d_top) cudaFree(d.d_top);
+    if (d.d_bottom) cudaFree(d.d_bottom);
+    d.d_top = nullptr;
+    d.d_bottom = nullptr;
+    d.T = d.Tpad = 0;
+    d.ensemble_bytes = 0;
+}
 
-    const uint32_t D = e->D, F = e->tuple_cls * 4;
-    const uint32_t Dk = std::max(D, 2u);
-    const uint32_t Dtop = Dk - 2;
-    const uint32_t nb = 1u << Dtop;
-    const uint32_t top_stride = std::max(1u, 1u << Dtop);
-    const uint32_t Tpad = (count + 7u) & ~7u;
-    const size_t wstride = (size_t)e->w_cls * 4, fstride = (size_t)e->f_cls * 8;
-    const uint32_t* Wall = reinterpret_cast<const uint32_t*>(wl);
-    const uint16_t* Fall = reinterpret_cast<const uint16_t*>(fl);
+int upload_ensemble(dte_engine* e, Dev& d, const PackedEnsemble& pk) {
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    CUDA_TRY(e, cudaDeviceSynchronize());           // nothing may still be walking the old ensemble
+    free_ensemble(d);
+    CUDA_TRY(e, cudaMalloc(&d.d_top, pk.top.size() * sizeof(uint2)));
+    CUDA_TRY(e, cudaMalloc(&d.d_bottom, pk.bottom.size() * sizeof(uint4)));
+    CUDA_TRY(e, cudaMemcpy(d.d_top, pk.top.data(), pk.top.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(d.d_bottom, pk.bottom.data(), pk.bottom.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    d.g = pk.g;
+    d.T = pk.T; d.Tpad = pk.Tpad; d.Dtop = pk.Dtop; d.top_stride = pk.top_stride; d.nb = pk.nb; d.wide = pk.wide;
+    d.ensemble_bytes = pk.top.size() * sizeof(uint2) + pk.bottom.size() * sizeof(uint4);
+    return DTE_OK;
+}
 
-    // pass 1: contract check + widest feature index
-    uint32_t max_f = 0;
-    for (uint32_t t = 0; t < count; ++t) {
-        const uint16_t* fi = Fall + (size_t)(first + t) * fstride;
-        for (uint32_t i = 0; i + 1 < (1u << D); ++i) {
-            const uint32_t f = fi[i] & 0x7FFu;
-            if (f >= F) return fail(e, DTE_ERR_UNSUPPORTED, "tree %u node %u: feature index %u >= %u features", first + t, i, f, F);
-            if (fi[i] & 0x4000u)
-                return fail(e, DTE_ERR_UNSUPPORTED, "tree %u node %u: bit 14 (next-node-is-leaf) set; complete trees only", first + t, i);
-            max_f = std::max(max_f, f);
+int pack_or_fail(dte_engine* e, const Geom& g, const unsigned char* wl, size_t n_wl, const unsigned char* fl, size_t n_fl,
+                 uint32_t first, uint32_t count, PackedEnsemble& pk) {
+    std::string msg;
+    const int rc = pack_ensemble(g, wl, n_wl, fl, n_fl, first, count, pk, msg);
+    if (rc) return fail(e, rc == -4 ? DTE_ERR_UNSUPPORTED : DTE_ERR_ARG, "%s", msg.c_str());
+    return DTE_OK;
+}
+
+// ---- partition of a run: registers 201 / 203 / 208-210 ---------------------------------------------
+struct Flags {
+    bool data_distributed, host_node, bcast_data, bcast_trees, aggreg, multiple, rx_enabled;
+    uint64_t batch_cls, chunk_w, chunk_f;
+    uint32_t ndev;
+};
+Flags decode_flags(const dte_engine* e) {
+    const uint64_t r201 = e->regs[1], r203 = e->regs[3];
+    Flags f;
+    f.data_distributed = r201 & 1; f.host_node = (r201 >> 1) & 1; f.bcast_data = (r201 >> 2) & 1;
+    f.bcast_trees = (r201 >> 3) & 1; f.aggreg = (r201 >> 4) & 1; f.multiple = (r201 >> 5) & 1;
+    f.rx_enabled = (r201 >> 6) & 1;
+    f.batch_cls = r201 >> 32;
+    f.chunk_w = (r203 & 0xFFFF) + 1;                // numcls_local_weights, "subtract in SW" (EngineCSR.sv:213)
+    f.chunk_f = (r203 >> 16) & 0xFFFF;
+    f.ndev = (uint32_t)std::max<uint64_t>(1, (r203 >> 32) & 0xFF);
+    return f;
+}
+
+// devices_list (registers 208-210): entry i, 5 bits in byte lane i%8 of register 208 + i/8 (EngineCSR.sv:250-296)
+uint32_t devices_list_entry(const dte_engine* e, uint32_t i) { return (uint32_t)((e->regs[8 + i / 8] >> (8 * (i % 8))) & 0x1F); }
+
+// Which device of this handle serves ring position `pos` (-1: none — another process owns it).
+int owner_of(const dte_engine* e, uint32_t pos) {
+    if (e->multi()) return pos < e->devs.size() ? e->pos2dev[pos] : -1;
+    return pos == e->node_index ? 0 : -1;
+}
+
+// Decide how the run is partitioned.  Single-device handles keep the raw RTL filter semantics (one process per
+// GPU replaying the same stream, dte_set_node); a multi-device handle supports exactly the two partitions of
+// SURVEY 8(e) and refuses the rest.
+int decide_partition(dte_engine* e, const Geom& g) {
+    const Flags f = decode_flags(e);
+    bool group = false, deal = false;
+    int pos2dev[kMaxRing];
+    const size_t G = e->devs.size();
+    for (uint32_t i = 0; i < (uint32_t)kMaxRing; ++i) pos2dev[i] = (int)i;
+    const bool split = f.multiple && f.ndev > 1;
+    if (e->multi()) {
+        if (!split) return fail(e, DTE_ERR_CONFIG, "a %zu-device handle needs multiple_nodes=1 (reg 201[5]) and numDevs=%zu (reg 203[39:32])", G, G);
+        if (f.ndev != G) return fail(e, DTE_ERR_CONFIG, "reg 203: numDevs=%u but the handle drives %zu devices", f.ndev, G);
+        bool any = false;
+        for (uint32_t i = 0; i < G; ++i) any |= devices_list_entry(e, i) != 0;
+        if (any) {                                   // programmed: must be a permutation of the device IDs 0..G-1
+            std::vector<int> seen(G, 0);
+            for (uint32_t i = 0; i < G; ++i) {
+                const uint32_t id = devices_list_entry(e, i);
+                if (id >= G || seen[id]++) return fail(e, DTE_ERR_CONFIG, "registers 208-210: devices_list[%u]=%u is not a permutation of 0..%zu", i, id, G - 1);
+                pos2dev[i] = (int)id;
+            }
         }
-    }
-    const bool wide = max_f >= 512;
-    const uint32_t BV = wide ? 4 : 2;
-
-    std::vector<uint2> top((size_t)Tpad * top_stride, make_uint2(0u, 8u << 16));
-    std::vector<uint4> bot((size_t)Tpad * nb * BV, make_uint4(0, 0, 0, 0));
-    std::vector<uint32_t> Wk((2u << Dk) - 1);
-    std::vector<uint16_t> Fk((1u << Dk) - 1);
-    for (uint32_t t = 0; t < count; ++t) {
-        const uint32_t* W = Wall + (size_t)(first + t) * wstride;
-        const uint16_t* FI = Fall + (size_t)(first + t) * fstride;
-        if (D == 1) {
-            // one comparison level: extend to two levels by giving both children of a dummy level
-            // the same leaf — the same function of x (see DESIGN.md "D = 1")
-            Wk[0] = W[0]; Wk[1] = 0; Wk[2] = 0;
-            Wk[3] = W[1]; Wk[4] = W[1]; Wk[5] = W[2]; Wk[6] = W[2];
-            Fk[0] = FI[0]; Fk[1] = 0; Fk[2] = 0;
+        if (f.bcast_trees && !f.bcast_data && !f.aggreg) {
+            deal = true;
+        } else if (!f.bcast_trees && f.bcast_data && f.aggreg) {
+            group = true;
+            for (size_t a = 0; a < G; ++a)
+                for (size_t b = 0; b < G; ++b) {
+                    int ok = 1;
+                    if (e->devs[a].ordinal != e->devs[b].ordinal) cudaDeviceCanAccessPeer(&ok, e->devs[a].ordinal, e->devs[b].ordinal);
+                    if (!ok) return fail(e, DTE_ERR_UNSUPPORTED, "GPU %d cannot access GPU %d peer-to-peer: the data broadcast and the ring combine need it",
+                                         e->devs[a].ordinal, e->devs[b].ordinal);
+                }
         } else {
-            std::copy(W, W + ((2u << D) - 1), Wk.begin());
-            std::copy(FI, FI + ((1u << D) - 1), Fk.begin());
+            return fail(e, DTE_ERR_CONFIG, "reg 201 = 0x%llx: a multi-device handle supports broadcast_trees (data dealt, no aggregate) or "
+                        "broadcast_data + aggreg_enabled (tree chunks, ring combine)", (unsigned long long)(e->regs[1] & 0xFF));
         }
-        uint2* tp = top.data() + (size_t)t * top_stride;
-        for (uint32_t n = 0; n + 1 < (1u << Dtop); ++n) {
-            const uint32_t f = Fk[n] & 0x7FFu, mr = (Fk[n] >> 13) & 1u;
-            tp[n] = make_uint2(Wk[n], f | ((8u + 8u * mr) << 16));
-        }
-        uint4* bp = bot.data() + (size_t)t * nb * BV;
-        for (uint32_t j = 0; j < nb; ++j) {
-            const uint32_t n = nb - 1 + j, l = 2 * n + 1, r = 2 * n + 2;
-            const uint32_t fp = Fk[n] & 0x7FFu, mp = (Fk[n] >> 13) & 1u;
-            const uint32_t fl_ = Fk[l] & 0x7FFu, ml = (Fk[l] >> 13) & 1u;
-            const uint32_t fr = Fk[r] & 0x7FFu, mr = (Fk[r] >> 13) & 1u;
-            const uint4 leaves = make_uint4(Wk[2 * l + 1], Wk[2 * l + 2], Wk[2 * r + 1], Wk[2 * r + 2]);
-            if (wide) {
-                bp[j * 4 + 0] = make_uint4(Wk[n], Wk[l], Wk[r], fp | (mp << 16));
-                bp[j * 4 + 1] = make_uint4(fl_ | (ml << 16), fr | (mr << 16), 0, 0);
-                bp[j * 4 + 2] = leaves;
-            } else {
-                const uint32_t pack = (fp | (mp << 9)) | ((fl_ | (ml << 9)) << 10) | ((fr | (mr << 9)) << 20);
-                bp[j * 2 + 0] = make_uint4(Wk[n], Wk[l], Wk[r], pack);
-                bp[j * 2 + 1] = leaves;
-            }
-        }
+    } else if (split && !f.bcast_data && !f.data_distributed) {
+        deal = true;                                 // this process keeps the batches of its own ring position
     }
-
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    free_ensemble(e);
-    CUDA_TRY(e, cudaMalloc(&e->d_top, top.size() * sizeof(uint2)));
-    CUDA_TRY(e, cudaMalloc(&e->d_bottom, bot.size() * sizeof(uint4)));
-    CUDA_TRY(e, cudaMemcpy(e->d_top, top.data(), top.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    CUDA_TRY(e, cudaMemcpy(e->d_bottom, bot.data(), bot.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-    e->T = count;
-    e->Tpad = Tpad;
-    e->Dtop = Dtop;
-    e->top_stride = top_stride;
-    e->nb = nb;
-    e->wide = wide;
-    e->ensemble_bytes = top.size() * sizeof(uint2) + bot.size() * sizeof(uint4);
-    e->prog_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_begin).count();
+    if (deal && (f.batch_cls == 0 || f.batch_cls % g.tuple_cls))
+        return fail(e, DTE_ERR_CONFIG, "reg 201: core_data_batch_cls=%llu must be a positive multiple of tuple_numcls=%u",
+                    (unsigned long long)f.batch_cls, g.tuple_cls);
+    e->ndev_ring = f.ndev;
+    e->group = group;
+    e->deal = deal;
+    e->deal_lines = deal ? f.batch_cls : 0;
+    memcpy(e->pos2dev, pos2dev, sizeof pos2dev);
     return DTE_OK;
 }
 
-// ---- launch planning ---------------------------------------------------------------------------
-size_t tile_smem(uint32_t F, int groups, int trees_per_stage, int nstages, uint32_t top_stride) {
-    return (size_t)kHdrBytes + (size_t)nstages * trees_per_stage * top_stride * 8 + (size_t)F * 32 * groups * 4;
+// ---- landing slots ------------------------------------------------------------------------------
+void free_slots(Dev& d) {
+    cudaSetDevice(d.ordinal);
+    for (Slot& s : d.slot) {
+        if (s.d_tup) cudaFree(s.d_tup);
+        if (s.d_sc) cudaFree(s.d_sc);
+        if (s.d_part) cudaFree(s.d_part);
+        if (s.d_lb) cudaFree(s.d_lb);
+        s.d_tup = nullptr; s.d_sc = nullptr; s.d_part = nullptr; s.d_lb = nullptr;
+        s.fill = s.walked = 0;
+    }
+    d.cap_tuples = 0;
+    d.slot_parts = false;
 }
 
-Plan make_plan(const dte_engine* e) {
-    Plan p;
-    p.wide = e->wide;
-    const uint32_t F = e->tuple_cls * 4;
-    const size_t budget = (size_t)e->smem_optin;
-    // tuple groups (32 tuples, F*128 B of shared memory each) that fit next to the ring
-    auto max_groups = [&](int ilp, int pair, int nstages) -> int {
-        const size_t fixed = tile_smem(F, 0, ilp * pair, nstages, e->top_stride);
-        if (fixed >= budget) return 0;
-        const int warp_cap = (pair == 4) ? 20 : (ilp == 8 ? 8 : 12);   // __launch_bounds__ of dt_walk_tile (+1 producer warp)
-        int g = (int)std::min<size_t>((size_t)(warp_cap / pair), (budget - fixed) / ((size_t)F * 128));
-        if (e->tune.warps) g = std::min(g, std::max(1, e->tune.warps / pair));
-        return g;
-    };
-    const int want = e->forced_variant;
-    const bool can_stage = e->Dtop >= 3;          // below that there is nothing worth staging
-    // staged candidates {trees per warp, warps per tuple group, ring stages}.  Measured on B200
-    // (profiles/r01_summary.md); the first candidate that fits with the most walks in flight wins.
-    const int cand[6][3] = {{4, 2, 1}, {2, 4, 1}, {8, 1, 1}, {8, 1, 2}, {4, 1, 2}, {4, 1, 1}};
-    Plan staged;
-    if (can_stage) {
-        int best = 0;
-        for (auto& c : cand) {
-            int ilp = e->tune.ilp ? e->tune.ilp : c[0];
-            int pair = e->tune.pair ? e->tune.pair : c[1];
-            int st = e->tune.stages ? e->tune.stages : c[2];
-            if (pair == 4) ilp = 2; else if (pair == 2) ilp = (ilp == 2) ? 2 : 4; else { pair = 1; if (ilp != 4 && ilp != 8) ilp = 8; }
-            st = std::max(1, std::min(st, 4));
-            const int g = max_groups(ilp, pair, st);
-            const int score = g * pair * ilp * 8 + (pair == 2 ? 4 : 0) - (pair == 4 ? 4 : 0) + st;
-            if (g >= 1 && score > best) {
-                best = score;
-                staged.variant = DTE_KERNEL_TILE_STAGED;
-                staged.ilp = ilp; staged.pair = pair; staged.nstages = st; staged.nwarps = g * pair; staged.wide = e->wide;
-                staged.smem = tile_smem(F, g, ilp * pair, st, e->top_stride);
-            }
-            if (e->tune.ilp && e->tune.stages && e->tune.pair) break;
+int ensure_slots(dte_engine* e, Dev& d, size_t cap, uint32_t F, bool parts) {
+    if (d.cap_tuples == cap && d.slot_F == F && (d.slot_parts || !parts)) return DTE_OK;
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    free_slots(d);
+    for (Slot& s : d.slot) {
+        CUDA_TRY(e, cudaMalloc(&s.d_tup, cap * F * 4));
+        CUDA_TRY(e, cudaMalloc(&s.d_sc, cap * 4));
+        CUDA_TRY(e, cudaMalloc(&s.d_lb, cap));
+        if (parts) CUDA_TRY(e, cudaMalloc(&s.d_part, cap * 4));
+    }
+    d.cap_tuples = cap;
+    d.slot_F = F;
+    d.slot_parts = parts;
+    d.cur = 0;
+    return DTE_OK;
+}
+
+size_t default_chunk(const dte_engine* e, uint32_t F) {
+    size_t c = e->opt_chunk_tuples ? e->opt_chunk_tuples : (e->tune.chunk ? e->tune.chunk : std::max<size_t>(4096, (64ull << 20) / (F * 4)));
+    return (std::max<size_t>(c, 4) + 3) & ~(size_t)3;      // whole result lines per slot
+}
+
+int ensure_ring(dte_engine* e, Dev& d, size_t cap_tuples) {
+    if (d.ring_cap >= cap_tuples) return DTE_OK;
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    if (d.h_ring) { cudaFreeHost(d.h_ring); d.h_ring = nullptr; d.ring_cap = 0; }
+    CUDA_TRY(e, cudaHostAlloc(reinterpret_cast<void**>(&d.h_ring), cap_tuples * 4, cudaHostAllocPortable));
+    d.ring_cap = cap_tuples;
+    return DTE_OK;
+}
+
+cudaEvent_t get_event(Dev& d) {
+    if (!d.ev_pool.empty()) {
+        cudaEvent_t ev = d.ev_pool.back();
+        d.ev_pool.pop_back();
+        return ev;
+    }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    return ev;
+}
+
+// Retire completed result copies of device d; block until its local result count reaches `need` (0 = only poll).
+int poll_dev(dte_engine* e, Dev& d, uint64_t need) {
+    if (!d.pend.empty()) cudaSetDevice(d.ordinal);
+    while (!d.pend.empty()) {
+        Pending& p = d.pend.front();
+        cudaError_t st = (d.res_done < need) ? cudaEventSynchronize(p.ev) : cudaEventQuery(p.ev);
+        if (st == cudaErrorNotReady) break;
+        if (st != cudaSuccess) return fail(e, DTE_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(st));
+        d.res_done = p.upto;
+        d.ev_pool.push_back(p.ev);
+        d.pend.pop_front();
+    }
+    return DTE_OK;
+}
+
+// D2H of `cnt` results of slot s starting at slot-local tuple `from`, into the device's current sink.
+int enqueue_results(dte_engine* e, Dev& d, Slot& s, size_t from, size_t cnt, bool labels) {
+    CUDA_TRY(e, cudaStreamWaitEvent(d.s_d2h, s.ev_walk, 0));
+    if (d.sink_sc) {
+        CUDA_TRY(e, cudaMemcpyAsync(d.sink_sc, s.d_sc + from, cnt * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+        d.sink_sc += cnt;
+        if (labels && d.sink_lb) {
+            CUDA_TRY(e, cudaMemcpyAsync(d.sink_lb, s.d_lb + from, cnt, cudaMemcpyDeviceToHost, d.s_d2h));
+            d.sink_lb += cnt;
         }
-    }
-    Plan tile;
-    {
-        const int ilp = (e->tune.ilp == 4) ? 4 : 8;
-        const int g = max_groups(ilp, 1, 0);
-        if (g >= 1) {
-            tile.variant = DTE_KERNEL_TILE; tile.ilp = ilp; tile.pair = 1; tile.nstages = 0; tile.nwarps = g; tile.wide = e->wide;
-            tile.smem = tile_smem(F, g, ilp, 0, e->top_stride);
-        }
-    }
-    if (want == DTE_KERNEL_TILE_STAGED && staged.nwarps >= 1) return staged;
-    if (want == DTE_KERNEL_TILE && tile.nwarps >= 1) return tile;
-    if (want == DTE_KERNEL_GENERIC) return p;
-    // AUTO (or a forced variant that does not fit): staged > tile > generic
-    if (staged.nwarps >= 2) return staged;
-    if (tile.nwarps >= 1) return tile;
-    return p;
-}
-
-template <int ILP, int P, bool STAGED, bool WIDE, int NT>
-cudaError_t launch_tile_nt(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
-    auto k = dt_walk_tile<ILP, P, STAGED, WIDE, NT>;
-    cudaError_t rc = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (rc != cudaSuccess) return rc;
-    k<<<grid, threads, smem, st>>>(wp);
-    return cudaGetLastError();
-}
-// thread-bound classes (see dt_walk_tile): <= 12 warps -> the 168-register instantiation, else the wide one
-template <int ILP, int P, bool STAGED, bool WIDE>
-cudaError_t launch_tile(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
-    constexpr int NT_MAX = P == 4 ? 672 : (ILP == 8 ? 288 : 416);
-    if constexpr (NT_MAX > 384) {
-        if (threads <= 384) return launch_tile_nt<ILP, P, STAGED, WIDE, 384>(wp, grid, threads, smem, st);
-    }
-    return launch_tile_nt<ILP, P, STAGED, WIDE, NT_MAX>(wp, grid, threads, smem, st);
-}
-
-int launch_walk(dte_engine* e, const void* d_tuples, size_t n, float* d_scores, uint8_t* d_labels, cudaStream_t st,
-                bool accumulate = false) {
-    if (!e->d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
-    if (n == 0) return DTE_OK;
-    const Plan pl = make_plan(e);
-    WalkParams wp;
-    wp.top = e->d_top;
-    wp.bottom = e->d_bottom;
-    wp.tuples = static_cast<const float*>(d_tuples);
-    wp.scores = d_scores;
-    wp.labels = d_labels;
-    wp.n = n;
-    wp.F = e->tuple_cls * 4;
-    wp.Dtop = e->Dtop;
-    wp.top_stride = e->top_stride;
-    wp.nb = e->nb;
-    // slots beyond S are never issued (DTPU.sv:519-531); groups past the last tree add exact zeros
-    wp.groups = (uint32_t)std::min<uint64_t>((uint64_t)e->S * e->K, e->Tpad / 8);
-    wp.K = e->K;
-    wp.missing = e->missing;
-    wp.nwarps = (uint32_t)pl.nwarps;
-    wp.nstages = (uint32_t)pl.nstages;
-    wp.accumulate = accumulate ? 1u : 0u;
-    wp.wide_rows = (wp.F % 8 == 0 && (reinterpret_cast<uintptr_t>(d_tuples) & 31u) == 0) ? 1u : 0u;
-    wp.fill_split = e->tune.fill ? 1u : 0u;      // DTE_TUNE fill=1: one bulk copy per tree instead of one per stage
-    // phased refill needs >= 3 staged levels and at most 4 ring stages (16 mbarriers in the header)
-    // Measured (profiles/r01_summary.md): +7 % at D = 12 (64 KiB stage), -4 % at D <= 10 (<= 16 KiB stage, the
-    // refill is already cheap there and the extra barrier hand-offs cost more than they hide).
-    const bool phased = e->tune.phased >= 1 || (e->tune.phased == -1 && e->Dtop >= 10);
-    // part A = levels 0..Lw; DTE_TUNE phased=k moves the split k-1 levels further up (smaller part A)
-    const uint32_t up = e->tune.phased > 1 ? (uint32_t)e->tune.phased - 1 : 0;
-    wp.Lw = (phased && e->Dtop >= 3 + up && pl.nstages <= 4) ? e->Dtop - 3 - up : 0xFFFFFFFFu;
-    wp.tiles = 0;
-    cudaError_t rc;
-    if (pl.variant == DTE_KERNEL_GENERIC) {
-        const int threads = 128;
-        const unsigned long long blocks = (n + threads - 1) / threads;
-        if (blocks > 0x7FFFFFFFull) return fail(e, DTE_ERR_ARG, "batch too large for one launch");
-        if (pl.wide) dt_walk_generic<true><<<(unsigned)blocks, threads, 0, st>>>(wp);
-        else dt_walk_generic<false><<<(unsigned)blocks, threads, 0, st>>>(wp);
-        rc = cudaGetLastError();
     } else {
-        const size_t M = 32ull * (pl.nwarps / pl.pair);
-        const unsigned long long tiles = (n + M - 1) / M;
-        if (tiles > 0xFFFFFFFFull) return fail(e, DTE_ERR_ARG, "batch too large for one launch");
-        wp.tiles = (uint32_t)tiles;
-        const int grid = (int)std::min<unsigned long long>(tiles, (unsigned long long)e->sm_count);
-        const bool staged = pl.variant == DTE_KERNEL_TILE_STAGED;
-        const int threads = 32 * (pl.nwarps + (staged ? 1 : 0));
-        const size_t sm = pl.smem;
-#define DTE_LAUNCH(ILP_, P_, ST_) (pl.wide ? launch_tile<ILP_, P_, ST_, true>(wp, grid, threads, sm, st) \
-                                           : launch_tile<ILP_, P_, ST_, false>(wp, grid, threads, sm, st))
-        if (staged) {
-            if (pl.ilp == 8) rc = DTE_LAUNCH(8, 1, true);
-            else if (pl.pair == 4) rc = DTE_LAUNCH(2, 4, true);
-            else if (pl.pair == 2 && pl.ilp == 2) rc = DTE_LAUNCH(2, 2, true);
-            else if (pl.pair == 2) rc = DTE_LAUNCH(4, 2, true);
-            else rc = DTE_LAUNCH(4, 1, true);
-        } else {
-            if (pl.ilp == 8) rc = DTE_LAUNCH(8, 1, false);
-            else rc = DTE_LAUNCH(4, 1, false);
+        size_t pos = (size_t)(d.res_enq % d.ring_cap), left = cnt, off = from;
+        while (left) {                               // the ring may wrap
+            const size_t run = std::min(left, d.ring_cap - pos);
+            CUDA_TRY(e, cudaMemcpyAsync(d.h_ring + pos, s.d_sc + off, run * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+            left -= run; off += run; pos = 0;
         }
-#undef DTE_LAUNCH
     }
-    if (rc != cudaSuccess) return fail(e, DTE_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(rc));
-    e->kernel_launches++;
+    CUDA_TRY(e, cudaEventRecord(s.ev_d2h, d.s_d2h));
+    cudaEvent_t ev = get_event(d);
+    CUDA_TRY(e, cudaEventRecord(ev, d.s_d2h));
+    d.res_enq += cnt;
+    d.pend.push_back({ev, d.res_enq});
     return DTE_OK;
 }
 
-int ensure_chunk_buffers(dte_engine* e, size_t cap, uint32_t F) {
-    if (e->chunk_cap >= cap && e->chunk_F == F) return DTE_OK;
-    for (int b = 0; b < kNumBuf; ++b) {
-        if (e->d_tup[b]) cudaFree(e->d_tup[b]);
-        if (e->d_sc[b]) cudaFree(e->d_sc[b]);
-        if (e->d_lb[b]) cudaFree(e->d_lb[b]);
-        e->d_tup[b] = nullptr; e->d_sc[b] = nullptr; e->d_lb[b] = nullptr;
-    }
-    e->chunk_cap = 0;
-    for (int b = 0; b < kNumBuf; ++b) {
-        CUDA_TRY(e, cudaMalloc(&e->d_tup[b], cap * F * 4));
-        CUDA_TRY(e, cudaMalloc(&e->d_sc[b], cap * 4));
-        CUDA_TRY(e, cudaMalloc(&e->d_lb[b], cap));
-    }
-    e->chunk_cap = cap;
-    e->chunk_F = F;
+// Walk the whole tuples that have landed in slot b of device d since the last submit and queue their results.
+int submit_dev(dte_engine* e, Dev& d, int b) {
+    Slot& s = d.slot[b];
+    const size_t tb = d.g.tuple_bytes();
+    if (!d.cap_tuples || !tb) return DTE_OK;
+    const size_t whole = s.fill / tb, cnt = whole - s.walked;
+    if (!cnt) return DTE_OK;
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    CUDA_TRY(e, cudaEventRecord(s.ev_land, d.s_h2d));
+    CUDA_TRY(e, cudaStreamWaitEvent(d.s_main, s.ev_land, 0));
+    CUDA_TRY(e, cudaStreamWaitEvent(d.s_main, s.ev_d2h, 0));        // score buffer of this slot drained
+    const bool labels = d.sink_sc && d.sink_lb;
+    const char* why = nullptr;
+    cudaError_t rc = launch_walk(d, e->tune, e->forced_variant, s.d_tup + s.walked * tb, cnt, s.d_sc + s.walked,
+                                 labels ? s.d_lb + s.walked : nullptr, d.s_main, false, &why);
+    if (rc != cudaSuccess) return fail(e, why ? DTE_ERR_ARG : DTE_ERR_CUDA, "walk kernel launch failed: %s", why ? why : cudaGetErrorString(rc));
+    CUDA_TRY(e, cudaEventRecord(s.ev_walk, d.s_main));
+    TRY(enqueue_results(e, d, s, s.walked, cnt, labels));
+    s.walked = whole;
+    e->tuples_out += cnt;
     return DTE_OK;
 }
 
-// Host buffers in, host buffers out: H2D of chunk i+1, walk of chunk i and D2H of chunk i-1 overlap.
+void advance_slot(Dev& d) {
+    d.cur = (d.cur + 1) % kNumSlots;
+    d.slot[d.cur].fill = 0;
+    d.slot[d.cur].walked = 0;
+}
+
+// Land `bytes` of the tuple stream on device d (H2D straight from the caller's buffer — pinned memory is DMA'd
+// in place, pageable memory goes through the driver's staging).  Full slots are submitted as they fill.
+int land_dev(dte_engine* e, Dev& d, const unsigned char* src, size_t bytes) {
+    const size_t cap_bytes = d.cap_tuples * d.g.tuple_bytes();
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    while (bytes) {
+        Slot& s = d.slot[d.cur];
+        if (s.fill == 0) CUDA_TRY(e, cudaStreamWaitEvent(d.s_h2d, s.ev_walk, 0));   // previous walk done with this buffer
+        const size_t take = std::min(bytes, cap_bytes - s.fill);
+        CUDA_TRY(e, cudaMemcpyAsync(s.d_tup + s.fill, src, take, cudaMemcpyHostToDevice, d.s_h2d));
+        s.fill += take;
+        src += take;
+        bytes -= take;
+        if (s.fill == cap_bytes) {
+            TRY(submit_dev(e, d, d.cur));
+            advance_slot(d);
+        }
+    }
+    return DTE_OK;
+}
+
+// ---- ensemble-sharded group: every device sees every tuple, partial scores are ring-combined ---------
+Dev& host_dev(dte_engine* e) { return e->devs[(size_t)e->pos2dev[0]]; }
+const Dev& host_dev(const dte_engine* e) { return e->devs[(size_t)e->pos2dev[0]]; }
+
+int nccl_setup(dte_engine* e) {
+    if (!e->nccl_comms.empty()) return DTE_OK;
+    if (!e->nccl.load()) return fail(e, DTE_ERR_UNSUPPORTED, "DTE_OPT_COMBINE=1 needs libnccl.so.2 (dlopen failed)");
+    const int G = (int)e->devs.size();
+    std::vector<int> ords((size_t)G);
+    for (int r = 0; r < G; ++r) ords[(size_t)r] = e->devs[(size_t)e->pos2dev[r]].ordinal;       // NCCL rank = ring position
+    e->nccl_comms.assign((size_t)G, nullptr);
+    const int rc = e->nccl.CommInitAll(e->nccl_comms.data(), G, ords.data());
+    if (rc) {
+        e->nccl_comms.clear();
+        return fail(e, DTE_ERR_CUDA, "ncclCommInitAll failed: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(rc) : "?");
+    }
+    return DTE_OK;
+}
+
+int submit_group(dte_engine* e, int b) {
+    const size_t G = e->devs.size();
+    Dev& h = host_dev(e);
+    const size_t tb = h.g.tuple_bytes();
+    if (!h.cap_tuples || !tb) return DTE_OK;
+    const size_t whole = h.slot[b].fill / tb, walked = h.slot[b].walked, cnt = whole - walked;
+    if (!cnt) return DTE_OK;
+    for (Dev& d : e->devs) {
+        CUDA_TRY(e, cudaSetDevice(d.ordinal));
+        CUDA_TRY(e, cudaEventRecord(d.slot[b].ev_land, d.s_h2d));
+    }
+    for (Dev& d : e->devs) {
+        Slot& s = d.slot[b];
+        CUDA_TRY(e, cudaSetDevice(d.ordinal));
+        for (Dev& src : e->devs) CUDA_TRY(e, cudaStreamWaitEvent(d.s_main, src.slot[b].ev_land, 0));   // every piece has landed here
+        CUDA_TRY(e, cudaStreamWaitEvent(d.s_main, h.slot[b].ev_comb, 0));    // the previous combine is done with our partials
+        const char* why = nullptr;
+        cudaError_t rc = launch_walk(d, e->tune, e->forced_variant, s.d_tup + walked * tb, cnt, s.d_part + walked, nullptr, d.s_main, false, &why);
+        if (rc != cudaSuccess) return fail(e, why ? DTE_ERR_ARG : DTE_ERR_CUDA, "walk kernel launch failed: %s", why ? why : cudaGetErrorString(rc));
+        CUDA_TRY(e, cudaEventRecord(s.ev_walk, d.s_main));
+        s.walked = whole;
+    }
+    Slot& hs = h.slot[b];
+    const bool labels = h.sink_sc && h.sink_lb;
+    CUDA_TRY(e, cudaSetDevice(h.ordinal));
+    CUDA_TRY(e, cudaStreamWaitEvent(h.s_main, hs.ev_d2h, 0));
+    if (!e->combine_nccl) {
+        for (Dev& d : e->devs) CUDA_TRY(e, cudaStreamWaitEvent(h.s_main, d.slot[b].ev_walk, 0));
+        RingParts parts;
+        for (size_t r = 0; r < G; ++r) parts.p[r] = e->devs[(size_t)e->pos2dev[r]].slot[b].d_part + walked;   // ring order, host first
+        const unsigned blocks = (unsigned)std::min<size_t>((cnt / 4 + 255) / 256 + 1, (size_t)h.sm_count * 8);
+        ring_combine_kernel<<<blocks, 256, 0, h.s_main>>>(parts, (int)G, hs.d_sc + walked, labels ? hs.d_lb + walked : nullptr, cnt);
+        CUDA_TRY(e, cudaGetLastError());
+        h.kernel_launches++;
+    } else {
+        TRY(nccl_setup(e));
+        int rc = e->nccl.GroupStart();
+        for (size_t r = 0; r < G && !rc; ++r) {
+            Dev& d = e->devs[(size_t)e->pos2dev[r]];
+            rc = e->nccl.Reduce(d.slot[b].d_part + walked, hs.d_sc + walked, cnt, kNcclFloat32, kNcclSum, 0, e->nccl_comms[r], d.s_main);
+        }
+        const int rc2 = e->nccl.GroupEnd();
+        if (rc || rc2) return fail(e, DTE_ERR_CUDA, "ncclReduce failed: %s", e->nccl.GetErrorString ? e->nccl.GetErrorString(rc ? rc : rc2) : "?");
+        CUDA_TRY(e, cudaSetDevice(h.ordinal));
+        if (labels) {
+            labels_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h.s_main>>>(hs.d_sc + walked, hs.d_lb + walked, cnt);
+            CUDA_TRY(e, cudaGetLastError());
+        }
+        for (Dev& d : e->devs) {                     // the reduce read d_part on every device's stream
+            CUDA_TRY(e, cudaSetDevice(d.ordinal));
+            CUDA_TRY(e, cudaEventRecord(d.slot[b].ev_walk, d.s_main));
+        }
+        CUDA_TRY(e, cudaSetDevice(h.ordinal));
+        for (Dev& d : e->devs) CUDA_TRY(e, cudaStreamWaitEvent(h.s_main, d.slot[b].ev_walk, 0));
+    }
+    CUDA_TRY(e, cudaEventRecord(hs.ev_comb, h.s_main));
+    CUDA_TRY(e, cudaEventRecord(hs.ev_walk, h.s_main));           // results of this slot are final after the combine
+    TRY(enqueue_results(e, h, hs, walked, cnt, labels));
+    e->tuples_out += cnt;
+    return DTE_OK;
+}
+
+// Broadcast landing (InputDistributor.sv:199-204 over NVLink instead of the SL3 ring): device g uploads the
+// g-th piece of the block over ITS OWN PCIe link and pushes it to every peer with peer-to-peer copies.
+int land_group(dte_engine* e, const unsigned char* src, size_t bytes) {
+    const size_t G = e->devs.size();
+    Dev& h = host_dev(e);
+    const size_t cap_bytes = h.cap_tuples * h.g.tuple_bytes();
+    static const size_t kMinPiece = 256u << 10;
+    uint32_t rot = 0;
+    while (bytes) {
+        const int b = h.cur;
+        const size_t fill = h.slot[b].fill;
+        if (fill == 0) {
+            for (Dev& d : e->devs) {                 // every copy stream writes into every device's slot b
+                CUDA_TRY(e, cudaSetDevice(d.ordinal));
+                for (Dev& o : e->devs) CUDA_TRY(e, cudaStreamWaitEvent(d.s_h2d, o.slot[b].ev_walk, 0));
+            }
+        }
+        const size_t take = std::min(bytes, cap_bytes - fill);
+        const size_t npieces = std::max<size_t>(1, std::min(G, take / kMinPiece));
+        size_t off = 0;
+        for (size_t pc = 0; pc < npieces; ++pc) {
+            const size_t len = (pc + 1 == npieces) ? take - off : ((take / npieces) & ~(size_t)15);
+            Dev& d = e->devs[(pc + rot) % G];
+            CUDA_TRY(e, cudaSetDevice(d.ordinal));
+            unsigned char* mine = d.slot[b].d_tup + fill + off;
+            CUDA_TRY(e, cudaMemcpyAsync(mine, src + off, len, cudaMemcpyHostToDevice, d.s_h2d));
+            for (Dev& o : e->devs) {
+                if (&o == &d) continue;
+                if (o.ordinal == d.ordinal)
+                    CUDA_TRY(e, cudaMemcpyAsync(o.slot[b].d_tup + fill + off, mine, len, cudaMemcpyDeviceToDevice, d.s_h2d));
+                else
+                    CUDA_TRY(e, cudaMemcpyPeerAsync(o.slot[b].d_tup + fill + off, o.ordinal, mine, d.ordinal, len, d.s_h2d));
+            }
+            off += len;
+        }
+        if (npieces < G) rot = (rot + (uint32_t)npieces) % (uint32_t)G;
+        for (Dev& d : e->devs) d.slot[b].fill = fill + take;
+        src += take;
+        bytes -= take;
+        if (fill + take == cap_bytes) {
+            TRY(submit_group(e, b));
+            for (Dev& d : e->devs) advance_slot(d);
+        }
+    }
+    return DTE_OK;
+}
+
+// ---- run-level helpers ----------------------------------------------------------------------------
+int flush_all(dte_engine* e) {
+    if (e->group) return submit_group(e, host_dev(e).cur);
+    for (Dev& d : e->devs) TRY(submit_dev(e, d, d.cur));
+    return DTE_OK;
+}
+
+// wait until the source buffers of every enqueued H2D may be reused by the caller
+int sync_sources(dte_engine* e) {
+    for (Dev& d : e->devs) {
+        CUDA_TRY(e, cudaSetDevice(d.ordinal));
+        CUDA_TRY(e, cudaStreamSynchronize(d.s_h2d));
+    }
+    return DTE_OK;
+}
+
+int drain_all(dte_engine* e) {
+    TRY(flush_all(e));
+    for (Dev& d : e->devs) {
+        CUDA_TRY(e, cudaSetDevice(d.ordinal));
+        CUDA_TRY(e, cudaStreamSynchronize(d.s_h2d));
+        CUDA_TRY(e, cudaStreamSynchronize(d.s_main));
+        CUDA_TRY(e, cudaStreamSynchronize(d.s_d2h));
+        TRY(poll_dev(e, d, 0));
+    }
+    return DTE_OK;
+}
+
+bool fragment_pending(const dte_engine* e) {
+    for (const Dev& d : e->devs)
+        if (d.cap_tuples && d.g.tuple_cls && d.slot[d.cur].fill % d.g.tuple_bytes()) return true;
+    return false;
+}
+
+void reset_pipeline(Dev& d) {
+    for (Slot& s : d.slot) { s.fill = 0; s.walked = 0; }
+    d.cur = 0;
+    d.sink_sc = nullptr;
+    d.sink_lb = nullptr;
+    d.res_enq = d.res_done = 0;
+    d.tuples_landed = 0;
+}
+
+// Results exposed by this handle, in order: tuple i lives on device dev at local index loc.
+void locate_result(const dte_engine* e, uint64_t i, int& dev, uint64_t& loc) {
+    if (e->multi() && e->deal) {
+        const uint64_t bt = e->deal_lines / e->g.tuple_cls, G = e->devs.size();
+        const uint64_t q = i / bt;
+        dev = e->pos2dev[q % G];
+        loc = (q / G) * bt + i % bt;
+    } else {
+        dev = e->group ? e->pos2dev[0] : 0;
+        loc = i;
+    }
+}
+// how many leading results (in exposed order) a per-device local count stands for
+uint64_t global_prefix(const dte_engine* e, bool completed) {
+    auto cnt = [&](const Dev& d) { return completed ? d.res_done : d.res_enq; };
+    if (e->multi() && e->deal) {
+        const uint64_t bt = e->deal_lines / e->g.tuple_cls, G = e->devs.size();
+        uint64_t best = ~0ull;
+        for (uint64_t r = 0; r < G; ++r) {           // first missing tuple of ring position r, as a global index
+            const uint64_t c = cnt(e->devs[(size_t)e->pos2dev[r]]);
+            best = std::min(best, (c / bt * G + r) * bt + c % bt);
+        }
+        return best;
+    }
+    return cnt(e->devs[(size_t)(e->group ? e->pos2dev[0] : 0)]);
+}
+
+int prepare_data_phase(dte_engine* e, bool need_ring) {
+    const uint32_t F = e->g.F();
+    const size_t cap = default_chunk(e, F);
+    for (Dev& d : e->devs) {
+        TRY(ensure_slots(e, d, cap, F, e->group));
+        d.g.K = e->g.K; d.g.S = e->g.S; d.g.missing = e->g.missing;     // summation geometry of THIS run
+    }
+    if (need_ring) {
+        // result queue: reg 207 says how many result lines the run produces; bounded either way
+        uint64_t lines = e->opt_queue_lines ? e->opt_queue_lines : (e->regs[7] & 0xFFFFFFFFull) + 64;
+        if (!e->opt_queue_lines) lines = std::max<uint64_t>(lines, 1u << 18);
+        lines = std::min<uint64_t>(std::max<uint64_t>(lines, 16), 1u << 26);
+        e->ring_cap = lines * 4;
+        const uint64_t G = e->devs.size();
+        const uint64_t bt = e->deal ? e->deal_lines / e->g.tuple_cls : 0;
+        for (Dev& d : e->devs) {
+            const bool has_results = !e->group || &d == &host_dev(e);
+            if (!has_results) continue;
+            const uint64_t per = (e->multi() && e->deal) ? e->ring_cap / G + 2 * bt + cap : e->ring_cap + cap;
+            TRY(ensure_ring(e, d, per));
+        }
+    }
+    return DTE_OK;
+}
+
+// Host buffers in, host buffers out (fast path, no line framing): the same landing pipeline with the caller's
+// score buffer as the direct sink.  Multi-device: chunks round-robin over the devices (trees replicated) or every
+// chunk broadcast to all of them (tree chunks + ring combine).
 int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_scores, uint8_t* h_labels) {
-    if (!e->d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
+    Geom g;
+    TRY(decode_geom(e, g));
+    TRY(check_resident(e, g));
     if (n == 0) return DTE_OK;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    const uint32_t F = e->tuple_cls * 4;
-    size_t chunk = e->tune.chunk ? e->tune.chunk : std::max<size_t>(4096, (64ull << 20) / (F * 4));
-    chunk = std::min(chunk, n);
-    int rc = ensure_chunk_buffers(e, chunk, F);
-    if (rc) return rc;
-    const size_t nchunks = (n + chunk - 1) / chunk;
-    CUDA_TRY(e, cudaEventRecord(e->ev_t0, e->s_main));
-    for (size_t i = 0; i < nchunks; ++i) {
-        const int b = (int)(i % kNumBuf);
-        const size_t off = i * chunk, cnt = std::min(chunk, n - off);
-        if (i >= (size_t)kNumBuf) {
-            CUDA_TRY(e, cudaStreamWaitEvent(e->s_h2d, e->ev_comp[b], 0));   // tuple buffer b free again
-            CUDA_TRY(e, cudaStreamWaitEvent(e->s_main, e->ev_d2h[b], 0));   // score buffer b drained
-        }
-        CUDA_TRY(e, cudaMemcpyAsync(e->d_tup[b], h_tuples + off * F * 4, cnt * F * 4, cudaMemcpyHostToDevice, e->s_h2d));
-        CUDA_TRY(e, cudaEventRecord(e->ev_h2d[b], e->s_h2d));
-        CUDA_TRY(e, cudaStreamWaitEvent(e->s_main, e->ev_h2d[b], 0));
-        rc = launch_walk(e, e->d_tup[b], cnt, e->d_sc[b], h_labels ? e->d_lb[b] : nullptr, e->s_main);
-        if (rc) return rc;
-        CUDA_TRY(e, cudaEventRecord(e->ev_comp[b], e->s_main));
-        CUDA_TRY(e, cudaStreamWaitEvent(e->s_d2h, e->ev_comp[b], 0));
-        CUDA_TRY(e, cudaMemcpyAsync(h_scores + off, e->d_sc[b], cnt * 4, cudaMemcpyDeviceToHost, e->s_d2h));
-        if (h_labels) CUDA_TRY(e, cudaMemcpyAsync(h_labels + off, e->d_lb[b], cnt, cudaMemcpyDeviceToHost, e->s_d2h));
-        CUDA_TRY(e, cudaEventRecord(e->ev_d2h[b], e->s_d2h));
+    if (e->state == dte_engine::ST_TREES) return fail(e, DTE_ERR_STATE, "infer_host while the tree stream is being received");
+    if (fragment_pending(e)) return fail(e, DTE_ERR_STATE, "a partial tuple is pending in the line stream");
+    TRY(drain_all(e));
+    const bool saved_group = e->group, saved_deal = e->deal;
+    e->g = g;
+    if (e->multi()) TRY(decide_partition(e, g));
+    TRY(prepare_data_phase(e, false));
+    const size_t tb = g.tuple_bytes();
+    std::vector<uint64_t> enq0(e->devs.size());
+    for (size_t i = 0; i < e->devs.size(); ++i) {
+        Dev& d = e->devs[i];
+        enq0[i] = d.res_enq;
+        CUDA_TRY(e, cudaSetDevice(d.ordinal));
+        CUDA_TRY(e, cudaEventRecord(d.ev_t0, d.s_main));
     }
-    CUDA_TRY(e, cudaEventRecord(e->ev_t1, e->s_main));
-    CUDA_TRY(e, cudaStreamSynchronize(e->s_h2d));
-    CUDA_TRY(e, cudaStreamSynchronize(e->s_main));
-    CUDA_TRY(e, cudaStreamSynchronize(e->s_d2h));
-    float ms = 0;
-    CUDA_TRY(e, cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1));
-    e->last_walk_ms = ms;
-    e->exec_ns += (double)ms * 1e6;
+    int rc = DTE_OK;
+    if (e->group) {
+        Dev& h = host_dev(e);
+        h.sink_sc = h_scores;
+        h.sink_lb = h_labels;
+        rc = land_group(e, h_tuples, n * tb);
+        if (!rc) rc = submit_group(e, h.cur);
+        for (Dev& d : e->devs)
+            if (d.slot[d.cur].fill) advance_slot(d);
+    } else {
+        const size_t chunk = e->devs[0].cap_tuples, G = e->devs.size();
+        size_t i = 0;
+        for (size_t off = 0; off < n && !rc; off += chunk, ++i) {
+            Dev& d = e->devs[i % G];
+            const size_t cnt = std::min(chunk, n - off);
+            d.sink_sc = h_scores + off;
+            d.sink_lb = h_labels ? h_labels + off : nullptr;
+            rc = land_dev(e, d, h_tuples + off * tb, cnt * tb);
+            if (!rc && d.slot[d.cur].fill) {         // a short last chunk
+                rc = submit_dev(e, d, d.cur);
+                advance_slot(d);
+            }
+        }
+    }
+    for (Dev& d : e->devs) {
+        cudaSetDevice(d.ordinal);
+        cudaEventRecord(d.ev_t1, d.s_main);
+    }
+    const int rc2 = drain_all(e);
+    float ms_max = 0;
+    for (size_t i = 0; i < e->devs.size(); ++i) {
+        Dev& d = e->devs[i];
+        float ms = 0;
+        cudaSetDevice(d.ordinal);
+        if (cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1) == cudaSuccess) d.last_walk_ms = ms;
+        ms_max = std::max(ms_max, ms);
+        d.sink_sc = nullptr; d.sink_lb = nullptr;
+        d.res_enq = d.res_done = enq0[i];            // direct-sink results are not part of the line-stream queue
+    }
+    e->last_walk_ms = ms_max;
+    if (!e->multi()) { e->group = saved_group; e->deal = saved_deal; }
+    if (rc || rc2) return rc ? rc : rc2;
     e->tuples_in += n;
-    e->tuples_out += n;
+    return DTE_OK;
+}
+
+cudaStream_t pick_stream(Dev& d, void* cuda_stream) { return cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : d.s_main; }
+
+int single_only(dte_engine* e, const char* what) {
+    if (e->multi()) return fail(e, DTE_ERR_UNSUPPORTED, "%s takes device pointers of ONE device: use a single-device handle (a multi-device handle takes host buffers)", what);
+    return DTE_OK;
+}
+
+int init_dev(Dev& d, int ordinal) {
+    d.ordinal = ordinal;
+    bool ok = cudaSetDevice(ordinal) == cudaSuccess &&
+              cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, ordinal) == cudaSuccess &&
+              cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&d.s_main, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&d.s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&d.ev_t0) == cudaSuccess && cudaEventCreate(&d.ev_t1) == cudaSuccess;
+    for (Slot& s : d.slot)
+        ok = ok && cudaEventCreateWithFlags(&s.ev_walk, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev_land, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.ev_comb, cudaEventDisableTiming) == cudaSuccess;
+    return ok ? DTE_OK : DTE_ERR_CUDA;
+}
+
+void destroy_dev(Dev& d) {
+    if (cudaSetDevice(d.ordinal) != cudaSuccess) return;
+    cudaDeviceSynchronize();
+    free_ensemble(d);
+    free_slots(d);
+    if (d.h_ring) cudaFreeHost(d.h_ring);
+    for (Slot& s : d.slot) {
+        if (s.ev_walk) cudaEventDestroy(s.ev_walk);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+        if (s.ev_land) cudaEventDestroy(s.ev_land);
+        if (s.ev_comb) cudaEventDestroy(s.ev_comb);
+    }
+    for (Pending& p : d.pend) cudaEventDestroy(p.ev);
+    for (cudaEvent_t ev : d.ev_pool) cudaEventDestroy(ev);
+    if (d.ev_t0) cudaEventDestroy(d.ev_t0);
+    if (d.ev_t1) cudaEventDestroy(d.ev_t1);
+    if (d.s_main) cudaStreamDestroy(d.s_main);
+    if (d.s_h2d) cudaStreamDestroy(d.s_h2d);
+    if (d.s_d2h) cudaStreamDestroy(d.s_d2h);
+}
+
+// Program the devices from the tree lines gathered per ring position.
+//   replicated: every device gets all trees;  chunked: ring position r gets the lines kept for it.
+int program_devices(dte_engine* e, const Geom& g) {
+    const Flags f = decode_flags(e);
+    const bool replicate = f.bcast_trees || f.ndev <= 1 || !f.multiple;
+    PackedEnsemble pk;
+    if (e->multi()) {
+        for (size_t r = 0; r < e->devs.size(); ++r) {
+            const size_t src = replicate ? 0 : r;
+            if (!replicate || r == 0) {
+                const size_t lw = e->tree_w[src].size() / 16, lf = e->tree_f[src].size() / 16;
+                if (!lw || !lf) return fail(e, DTE_ERR_CONFIG, "ring position %zu received no trees", r);
+                TRY(pack_or_fail(e, g, e->tree_w[src].data(), lw, e->tree_f[src].data(), lf, 0, 0, pk));
+            }
+            TRY(upload_ensemble(e, e->devs[(size_t)e->pos2dev[r]], pk));
+        }
+    } else {
+        const size_t src = replicate ? 0 : e->node_index;
+        const size_t lw = e->tree_w[src].size() / 16, lf = e->tree_f[src].size() / 16;
+        if (!lw || !lf) return fail(e, DTE_ERR_CONFIG, "node %u received no trees", e->node_index);
+        TRY(pack_or_fail(e, g, e->tree_w[src].data(), lw, e->tree_f[src].data(), lf, 0, 0, pk));
+        TRY(upload_ensemble(e, e->devs[0], pk));
+    }
+    return DTE_OK;
+}
+
+uint64_t cycles_of(const dte_engine* e, double ns) {
+    return e->cycle_mhz ? (uint64_t)(ns * 1e-3 * e->cycle_mhz) : (uint64_t)ns;
+}
+
+// tuples served by cluster 0: tuple i uses clusters (i*K)%8 .. +K-1 (Core.sv:305-316)
+uint64_t cluster0_tuples(const dte_engine* e) {
+    const Dev& h = e->devs[(size_t)(e->multi() ? e->pos2dev[0] : 0)];
+    return (h.tuples_landed * std::max(1u, e->g.K) + 7) / 8;
+}
+
+// process_done = total_pcie_out_cls_count == total_results_numcls (DTInference.sv:649-656); "produced" counts the
+// lines handed out plus the complete ones still queued
+int check_done(dte_engine* e, bool* done) {
+    const uint64_t want = e->regs[7] & 0xFFFFFFFFull;                           // reg 207[31:0]
+    if (e->done_latched) { *done = true; return DTE_OK; }
+    *done = false;
+    if (!want || !e->running || e->state != dte_engine::ST_DATA) return DTE_OK;
+    TRY(flush_all(e));
+    for (Dev& d : e->devs) TRY(poll_dev(e, d, 0));
+    const uint64_t produced = e->result_lines_out + (global_prefix(e, true) - e->res_read) / 4;
+    if (produced >= want) {
+        *done = true;
+        e->done_latched = true;
+        e->t_done = Clock::now();
+        e->running = false;
+        e->state = dte_engine::ST_IDLE;                                         // PCIeReceiver.sv:289-292
+        const uint64_t c0 = cluster0_tuples(e);
+        e->cum_c0 += c0;
+        e->cum_c0_lines += c0 * e->g.tuple_cls;
+        for (Dev& d : e->devs) d.tuples_landed = 0;
+    }
     return DTE_OK;
 }
 
@@ -491,60 +834,80 @@ int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_
 // =================================================================================================
 extern "C" {
 
-const char* dte_version(void) { return "dte-b200 0.1 (sm_100a)"; }
+const char* dte_version(void) { return "dte-b200 0.2 (sm_100a)"; }
 
-int dte_create(dte_t** engine, int gpu_ordinal) {
+int dte_create_multi(dte_t** engine, const int* gpu_ordinals, int n_gpus) {
     if (!engine) return DTE_ERR_ARG;
     *engine = nullptr;
+    if (!gpu_ordinals || n_gpus < 1 || n_gpus > kMaxRing) return DTE_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DTE_ERR_CUDA;   // no CPU fallback
-    if (gpu_ordinal < 0 || gpu_ordinal >= ndev) return DTE_ERR_ARG;
+    // an ordinal may appear more than once: several ring positions then share one GPU (how the multi-device
+    // logic is tested on a one-GPU box; the NCCL combine needs distinct GPUs)
+    for (int i = 0; i < n_gpus; ++i)
+        if (gpu_ordinals[i] < 0 || gpu_ordinals[i] >= ndev) return DTE_ERR_ARG;
     dte_engine* e = new (std::nothrow) dte_engine();
     if (!e) return DTE_ERR_NOMEM;
-    e->dev = gpu_ordinal;
     parse_tune(e->tune);
-    bool ok = cudaSetDevice(gpu_ordinal) == cudaSuccess &&
-              cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, gpu_ordinal) == cudaSuccess &&
-              cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, gpu_ordinal) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&e->s_main, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreate(&e->ev_t0) == cudaSuccess && cudaEventCreate(&e->ev_t1) == cudaSuccess;
-    for (int b = 0; ok && b < kNumBuf; ++b)
-        ok = cudaEventCreateWithFlags(&e->ev_h2d[b], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&e->ev_comp[b], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&e->ev_d2h[b], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) {
+    e->devs.resize((size_t)n_gpus);
+    for (uint32_t i = 0; i < (uint32_t)kMaxRing; ++i) e->pos2dev[i] = (int)i;
+    e->tree_w.resize(kMaxRing);
+    e->tree_f.resize(kMaxRing);
+    int rc = DTE_OK;
+    for (int i = 0; i < n_gpus && !rc; ++i) rc = init_dev(e->devs[(size_t)i], gpu_ordinals[i]);
+    if (!rc && n_gpus > 1) {
+        // peer access between all devices of the ring: the data broadcast and the ring combine ride NVLink
+        for (int a = 0; a < n_gpus; ++a)
+            for (int b = 0; b < n_gpus; ++b) {
+                if (gpu_ordinals[a] == gpu_ordinals[b]) continue;
+                int ok = 0;
+                cudaDeviceCanAccessPeer(&ok, gpu_ordinals[a], gpu_ordinals[b]);
+                if (!ok) continue;                   // refused later, only if a run needs it
+                cudaSetDevice(gpu_ordinals[a]);
+                if (cudaDeviceEnablePeerAccess(gpu_ordinals[b], 0) != cudaSuccess) cudaGetLastError();   // "already enabled" is fine
+            }
+    }
+    if (rc) {
+        for (Dev& d : e->devs) destroy_dev(d);
         delete e;
-        return DTE_ERR_CUDA;
+        return rc;
     }
     *engine = e;
     return DTE_OK;
 }
 
+int dte_create(dte_t** engine, int gpu_ordinal) { return dte_create_multi(engine, &gpu_ordinal, 1); }
+
 int dte_destroy(dte_t* e) {
     if (!e) return DTE_ERR_ARG;
-    cudaSetDevice(e->dev);
-    cudaDeviceSynchronize();
-    free_ensemble(e);
-    for (int b = 0; b < kNumBuf; ++b) {
-        if (e->d_tup[b]) cudaFree(e->d_tup[b]);
-        if (e->d_sc[b]) cudaFree(e->d_sc[b]);
-        if (e->d_lb[b]) cudaFree(e->d_lb[b]);
-        cudaEventDestroy(e->ev_h2d[b]);
-        cudaEventDestroy(e->ev_comp[b]);
-        cudaEventDestroy(e->ev_d2h[b]);
+    for (Dev& d : e->devs) {
+        cudaSetDevice(d.ordinal);
+        cudaDeviceSynchronize();
     }
-    cudaEventDestroy(e->ev_t0);
-    cudaEventDestroy(e->ev_t1);
-    cudaStreamDestroy(e->s_main);
-    cudaStreamDestroy(e->s_h2d);
-    cudaStreamDestroy(e->s_d2h);
+    if (!e->nccl_comms.empty() && e->nccl.CommDestroy)
+        for (void* c : e->nccl_comms)
+            if (c) e->nccl.CommDestroy(c);
+    for (Dev& d : e->devs) destroy_dev(d);
     delete e;
     return DTE_OK;
 }
 
 const char* dte_last_error(const dte_t* e) { return e ? e->err.c_str() : "null engine"; }
+
+int dte_set_option(dte_t* e, int option, uint64_t value) {
+    if (!e) return DTE_ERR_ARG;
+    switch (option) {
+        case DTE_OPT_CYCLE_MHZ: e->cycle_mhz = (uint32_t)value; break;
+        case DTE_OPT_COMBINE:
+            if (value > 1) return fail(e, DTE_ERR_ARG, "DTE_OPT_COMBINE: 0 (ring kernel) or 1 (NCCL reduce)");
+            e->combine_nccl = (int)value;
+            break;
+        case DTE_OPT_RESULT_QUEUE_LINES: e->opt_queue_lines = (size_t)value; break;
+        case DTE_OPT_CHUNK_TUPLES: e->opt_chunk_tuples = (size_t)value; break;
+        default: return fail(e, DTE_ERR_ARG, "unknown option %d", option);
+    }
+    return DTE_OK;
+}
 
 int dte_softreg_write(dte_t* e, uint32_t addr, uint64_t data) {
     if (!e) return DTE_ERR_ARG;
@@ -556,45 +919,86 @@ int dte_softreg_write(dte_t* e, uint32_t addr, uint64_t data) {
     if (!(data & 1)) return DTE_OK;
     // `start` (EngineCSR.sv:191-193): Core FSM, counters and schedules reset (Core.sv:168-187);
     // the PU tree memories are NOT cleared (DTPU.sv:307-319) -> the resident ensemble stays.
+    TRY(drain_all(e));                                    // results of an unfinished previous run are dropped
+    if (e->running) {                                     // cluster counters survive `start` (DTPUCluster.sv:85-97)
+        const uint64_t c0 = cluster0_tuples(e);
+        e->cum_c0 += c0;
+        e->cum_c0_lines += c0 * e->g.tuple_cls;
+    }
     e->lines_received = 0;
     e->cur_w = e->cur_f = e->cur_d = 0;
     e->cur_dev = 0;
-    e->local_w_lines = 0;
-    e->tree_lines.clear();
-    e->tuple_partial.clear();
-    e->result_words.clear();
-    e->result_read_pos = 0;
+    for (auto& v : e->tree_w) v.clear();
+    for (auto& v : e->tree_f) v.clear();
+    e->data_lines_in = 0;
+    e->res_read = 0;
     e->result_lines_out = 0;
     e->out_cl_count = 0;
-    const uint64_t r201 = e->regs[1];
-    const bool data_distributed = r201 & 1, host_node = (r201 >> 1) & 1, rx_enabled = (r201 >> 6) & 1;
+    e->prog_lines_local = e->sl3_lines_sent = e->sl3_res_lines = 0;
+    e->done_latched = false;
+    e->prog_seen = e->prog_open = false;
+    e->ring_cap = 0;
+    for (Dev& d : e->devs) reset_pipeline(d);
+    e->t_start = Clock::now();
+    e->running = true;
+    const Flags f = decode_flags(e);
     e->state = dte_engine::ST_IDLE;
-    if (rx_enabled) {                                       // PCIeReceiver.sv:218-227
-        if (host_node) e->state = dte_engine::ST_TREES;
-        else if (data_distributed) e->state = dte_engine::ST_DATA;
+    if (f.rx_enabled) {                                   // PCIeReceiver.sv:218-227
+        if (f.host_node) e->state = dte_engine::ST_TREES;
+        else if (f.data_distributed) e->state = dte_engine::ST_DATA;
     }
-    if (e->state == dte_engine::ST_DATA) {
-        int rc = decode_csr(e);
-        if (rc) { e->state = dte_engine::ST_IDLE; return rc; }
-        if (!e->d_top) { e->state = dte_engine::ST_IDLE; return fail(e, DTE_ERR_STATE, "start in data-only mode without a resident ensemble"); }
+    if (e->state == dte_engine::ST_IDLE) { e->running = false; return DTE_OK; }
+    // decode into locals; commit only when the whole configuration is accepted
+    Geom g;
+    int rc = decode_geom(e, g);
+    if (!rc) rc = decide_partition(e, g);
+    if (!rc && e->state == dte_engine::ST_DATA) {
+        rc = check_resident(e, g);
+        if (!rc) { e->g = g; rc = prepare_data_phase(e, true); }
     }
+    if (rc) { e->state = dte_engine::ST_IDLE; e->running = false; return rc; }
+    e->g = g;
     return DTE_OK;
 }
 
 int dte_softreg_read(dte_t* e, uint32_t addr, uint64_t* data) {
     if (!e || !data) return DTE_ERR_ARG;
+    const Clock::time_point now = Clock::now();
+    // appStatus (DTInference.sv:367-372): pairs of 32-bit debug counters, modelled from the run's counts
+    const uint32_t S = std::max(1u, e->g.S), tcl = std::max(1u, e->g.tuple_cls);
+    const Dev& h = e->devs[(size_t)(e->multi() ? e->pos2dev[0] : 0)];
+    const uint64_t n_t = h.tuples_landed;
+    const uint64_t c0 = e->running ? cluster0_tuples(e) : 0;
+    auto pair32 = [](uint64_t hi, uint64_t lo) { return ((hi & 0xFFFFFFFFull) << 32) | (lo & 0xFFFFFFFFull); };
     switch (addr) {
         case 220: *data = (uint64_t)e->state; break;                          // pcie_receiver_fsm_state
         case 221: *data = e->lines_received & 0xFFFFFFFFull; break;           // pcie_numcls_received
-        case 222: *data = (uint64_t)e->prog_ns; break;                        // progCycles (ns here)
-        case 223: *data = (uint64_t)e->exec_ns; break;                        // execCycles (ns here)
-        case 224: case 225: case 226: *data = 0; break;                       // SL3 tx counters: no ring traffic
-        case 121: *data = e->tuples_in & 0xFFFFFFFFull; break;                // appStatus: tuples received
-        case 122: *data = e->tuples_out & 0xFFFFFFFFull; break;               //            tuples emitted
-        case 123: *data = e->result_lines_out & 0xFFFFFFFFull; break;         //            result lines
-        case 124: *data = e->kernel_launches & 0xFFFFFFFFull; break;
-        case 125: *data = e->T; break;
-        case 126: *data = 0; break;                                            // res_lines_lost: never
+        case 222: {                                                            // progCycles (DTInference.sv:347-357)
+            double ns = 0;
+            if (e->prog_seen) ns = ns_since(e->t_prog0, e->prog_open ? now : e->t_prog1);
+            *data = cycles_of(e, ns) & 0xFFFFFFFFull;
+            break;
+        }
+        case 223: {                                                            // execCycles (:330-345): start -> process_done
+            double ns = 0;
+            if (e->running) ns = ns_since(e->t_start, now);
+            else if (e->done_latched) ns = ns_since(e->t_start, e->t_done);
+            *data = cycles_of(e, ns) & 0xFFFFFFFFull;
+            break;
+        }
+        case 224: *data = e->sl3_lines_sent & 0xFFFFFFFFull; break;           // num_sent_lines: lines that left for other devices
+        case 225: {                                                            // num_sent_packets (data_packet_numcls, reg 206[31:24])
+            const uint64_t pk = std::max<uint64_t>(1, (e->regs[6] >> 24) & 0xFF);
+            *data = ((e->sl3_lines_sent + pk - 1) / pk) & 0xFFFFFFFFull;
+            break;
+        }
+        case 226: *data = e->sl3_lines_sent & 0xFFFFFFFFull; break;           // packets_lines
+        case 121: *data = pair32(c0, e->cum_c0 + c0); break;                   // {cluster_out_valids, cluster_tuples_res_out[0]}
+        case 122: *data = pair32(n_t, (e->cum_c0 + c0) * S); break;            // {num_out_tuples, cluster_tree_res_out[0]}
+        case 123: *data = pair32(n_t * tcl, e->prog_lines_local); break;       // {data_lines, prog_lines}
+        case 124: *data = pair32(n_t, e->cum_c0 + c0); break;                  // {aggreg_tuples_in, cluster_reduce_tree_outs[0]}
+        case 125: *data = pair32(e->cum_c0 + c0, e->sl3_res_lines); break;     // {cluster_reduce_tree_outs_valids[0], sl3_res_lines}
+        case 126: *data = pair32(e->cum_c0 + c0, e->cum_c0_lines + c0 * tcl); break;   // {cluster_tuples_received[0], cluster_lines_received[0]}
         default: *data = 0xFFFFFFFFFFFFFFFFull; break;                         // EngineCSR.sv:123
     }
     return DTE_OK;
@@ -603,41 +1007,44 @@ int dte_softreg_read(dte_t* e, uint32_t addr, uint64_t* data) {
 int dte_stream_write(dte_t* e, const void* cl128, size_t n_lines) {
     if (!e || (!cl128 && n_lines)) return DTE_ERR_ARG;
     const unsigned char* p = static_cast<const unsigned char*>(cl128);
+    bool landed = false;
     while (n_lines) {
         if (e->state == dte_engine::ST_TREES) {
             const uint64_t total = e->regs[2] & 0xFFFFFFFFull, wtotal = e->regs[2] >> 32;   // reg 202
             if (total == 0 || wtotal == 0 || wtotal >= total)
                 return fail(e, DTE_ERR_CONFIG, "reg 202: total_num_trees_cls=%llu total_num_weights_cls=%llu",
                             (unsigned long long)total, (unsigned long long)wtotal);
-            // Multi-node chunking (PCIeReceiver.sv:241-264): unless broadcast_trees, the weights stream
-            // is cut every numcls_local_weights lines and the index stream every numcls_local_findexes
-            // lines, chunk i going to devices_list[i % numDevs]; entry 0 is the host node itself
-            // (:160-178).  Every process replays the SAME stream; engine g keeps the chunks of entry g.
-            const uint64_t r201 = e->regs[1], r203 = e->regs[3];
-            const bool multi = (r201 >> 5) & 1, bcast_trees = (r201 >> 3) & 1;
-            const uint64_t chunk_w = (r203 & 0xFFFF) + 1, chunk_f = (r203 >> 16) & 0xFFFF;
-            const uint32_t ndev = (uint32_t)std::max<uint64_t>(1, (r203 >> 32) & 0xFF);
-            const bool deal = multi && !bcast_trees && ndev > 1;
-            if (deal && (chunk_f == 0 || e->node_index >= ndev))
+            if (!e->prog_seen) { e->prog_seen = e->prog_open = true; e->t_prog0 = Clock::now(); }
+            // Chunking (PCIeReceiver.sv:241-264): unless broadcast_trees, the weights stream is cut every
+            // numcls_local_weights lines and the index stream every numcls_local_findexes lines, chunk i going to
+            // devices_list[i % numDevs]; entry 0 is the host node itself (:160-178).  currDevID keeps rotating
+            // from the weights into the index stream, as in the RTL.
+            const Flags f = decode_flags(e);
+            const bool cut = f.multiple && !f.bcast_trees && f.ndev > 1;
+            if (cut && (f.chunk_f == 0 || (!e->multi() && e->node_index >= f.ndev)))
                 return fail(e, DTE_ERR_CONFIG, "reg 203: numcls_local_findexes=%llu numDevs=%u node=%u",
-                            (unsigned long long)chunk_f, ndev, e->node_index);
+                            (unsigned long long)f.chunk_f, f.ndev, e->node_index);
             const size_t take = (size_t)std::min<uint64_t>(n_lines, total - e->lines_received);
-            if (!deal) {
-                e->tree_lines.insert(e->tree_lines.end(), p, p + take * 16);
-                e->local_w_lines += std::min<uint64_t>(take, wtotal > e->lines_received ? wtotal - e->lines_received : 0);
+            if (!cut) {
+                const uint64_t w_take = std::min<uint64_t>(take, wtotal > e->lines_received ? wtotal - e->lines_received : 0);
+                e->tree_w[0].insert(e->tree_w[0].end(), p, p + w_take * 16);
+                e->tree_f[0].insert(e->tree_f[0].end(), p + w_take * 16, p + take * 16);
+                e->prog_lines_local += take;
+                if (e->multi()) e->sl3_lines_sent += take;                       // broadcast to the ring as well
             } else {
                 for (size_t i = 0; i < take; ++i) {
                     const bool is_w = e->lines_received + i < wtotal;
-                    if (e->cur_dev == e->node_index) {
-                        e->tree_lines.insert(e->tree_lines.end(), p + i * 16, p + i * 16 + 16);
-                        if (is_w) e->local_w_lines++;
+                    if (owner_of(e, e->cur_dev) >= 0) {
+                        auto& v = is_w ? e->tree_w[e->cur_dev] : e->tree_f[e->cur_dev];
+                        v.insert(v.end(), p + i * 16, p + i * 16 + 16);
                     }
+                    if (e->cur_dev == (e->multi() ? 0u : e->node_index)) e->prog_lines_local++;
+                    if (e->cur_dev != 0) e->sl3_lines_sent++;
                     uint64_t& cnt = is_w ? e->cur_w : e->cur_f;
-                    if (++cnt == (is_w ? chunk_w : chunk_f)) {
+                    if (++cnt == (is_w ? f.chunk_w : f.chunk_f)) {
                         cnt = 0;
-                        e->cur_dev = (e->cur_dev + 1 == ndev) ? 0 : e->cur_dev + 1;
+                        e->cur_dev = (e->cur_dev + 1 == f.ndev) ? 0 : e->cur_dev + 1;
                     }
-                    if (is_w && e->lines_received + i + 1 == wtotal) { e->cur_dev = 0; e->cur_w = 0; }   // index stream restarts at the host
                 }
             }
             e->lines_received += take;
@@ -645,91 +1052,127 @@ int dte_stream_write(dte_t* e, const void* cl128, size_t n_lines) {
             n_lines -= take;
             if (e->lines_received == total) {
                 // prog_mode = (numcls_received < total_num_weights_cls), PCIeReceiver.sv:136-139
-                const size_t lw = (size_t)e->local_w_lines, lf = e->tree_lines.size() / 16 - lw;
-                int rc = (lw && lf) ? load_ensemble(e, e->tree_lines.data(), lw, e->tree_lines.data() + lw * 16, lf, 0, 0)
-                                    : fail(e, DTE_ERR_CONFIG, "node %u received no trees", e->node_index);
-                e->tree_lines.clear();
-                e->tree_lines.shrink_to_fit();
-                if (rc) { e->state = dte_engine::ST_IDLE; return rc; }
+                int rc = program_devices(e, e->g);
+                for (auto& v : e->tree_w) { v.clear(); v.shrink_to_fit(); }
+                for (auto& v : e->tree_f) { v.clear(); v.shrink_to_fit(); }
+                if (!rc) rc = prepare_data_phase(e, true);
+                e->t_prog1 = Clock::now();
+                e->prog_open = false;
+                if (rc) { e->state = dte_engine::ST_IDLE; e->running = false; return rc; }
                 e->state = dte_engine::ST_DATA;                                 // WAIT_DATA -> RECEIVE_DATA
                 e->cur_dev = 0;
                 e->cur_d = 0;
             }
         } else if (e->state == dte_engine::ST_DATA) {
-            const size_t tbytes = (size_t)e->tuple_cls * 16;
-            // Data dealing (PCIeReceiver.sv:298-307): unless broadcast_data, batches of core_data_batch_cls
-            // lines go round-robin over devices_list; this engine keeps the batches of its own entry.
-            const uint64_t r201d = e->regs[1];
-            const bool multi_d = (r201d >> 5) & 1, bcast_data = (r201d >> 2) & 1, distributed = r201d & 1;
-            const uint32_t ndev_d = (uint32_t)std::max<uint64_t>(1, (e->regs[3] >> 32) & 0xFF);
-            std::vector<unsigned char> mine;
-            const size_t lines_in = n_lines;
-            if (multi_d && !bcast_data && !distributed && ndev_d > 1) {
-                const uint64_t batch = r201d >> 32;
-                if (batch == 0 || batch % e->tuple_cls)
-                    return fail(e, DTE_ERR_CONFIG, "reg 201: core_data_batch_cls=%llu must be a positive multiple of tuple_numcls=%u",
-                                (unsigned long long)batch, e->tuple_cls);
-                mine.reserve(n_lines * 16 / ndev_d + 16);
-                for (size_t i = 0; i < n_lines; ++i) {
-                    if (e->cur_dev == e->node_index) mine.insert(mine.end(), p + i * 16, p + i * 16 + 16);
-                    if (++e->cur_d == batch) { e->cur_d = 0; e->cur_dev = (e->cur_dev + 1 == ndev_d) ? 0 : e->cur_dev + 1; }
+            // back-pressure: the result queue is bounded (pcie_full_out, PCIeReceiver.sv:126)
+            const size_t tcl = e->g.tuple_cls;
+            uint64_t in_engine = (e->data_lines_in + n_lines) / tcl;                         // results queued once these lines are in
+            if (!e->multi() && e->deal) in_engine = in_engine / e->ndev_ring + e->deal_lines / tcl;   // this node keeps 1/numDevs of them
+            in_engine = in_engine > e->res_read ? in_engine - e->res_read : 0;
+            if (in_engine > e->ring_cap)
+                return fail(e, DTE_ERR_BACKPRESSURE, "result queue full (%llu results would wait, capacity %llu): read result lines first",
+                            (unsigned long long)in_engine, (unsigned long long)e->ring_cap);
+            const size_t tb = e->g.tuple_bytes();
+            const uint64_t lines_before = e->data_lines_in;
+            if (e->group) {
+                // data broadcast (InputDistributor.sv:199-204): every device receives every line
+                TRY(land_group(e, p, n_lines * 16));
+                for (Dev& d : e->devs) d.tuples_landed = (e->data_lines_in + n_lines) * 16 / tb;
+                e->sl3_lines_sent += n_lines;
+            } else if (!e->deal) {
+                TRY(land_dev(e, e->devs[0], p, n_lines * 16));
+                e->devs[0].tuples_landed = (e->data_lines_in + n_lines) * 16 / tb;
+            } else {
+                // data dealing (PCIeReceiver.sv:298-307): batches of core_data_batch_cls lines round-robin over the ring
+                size_t left = n_lines;
+                const unsigned char* q = p;
+                while (left) {
+                    const size_t run = (size_t)std::min<uint64_t>(left, e->deal_lines - e->cur_d);
+                    const int dv = owner_of(e, e->cur_dev);
+                    if (dv >= 0) {
+                        Dev& d = e->devs[(size_t)dv];
+                        TRY(land_dev(e, d, q, run * 16));
+                        d.tuples_landed = d.slot[d.cur].fill / tb - d.slot[d.cur].walked + d.res_enq;   // whole tuples so far on this device
+                    }
+                    if (e->cur_dev != 0) e->sl3_lines_sent += run;
+                    e->cur_d += run;
+                    if (e->cur_d == e->deal_lines) { e->cur_d = 0; e->cur_dev = (e->cur_dev + 1 == e->ndev_ring) ? 0 : e->cur_dev + 1; }
+                    q += run * 16;
+                    left -= run;
                 }
-                p = mine.data();
-                n_lines = mine.size() / 16;
             }
-            // frame tuples by counting tuple_numcls lines (InputDistributor.sv:276-296)
-            std::vector<unsigned char>& part = e->tuple_partial;
-            const unsigned char* src = p;
-            size_t nbytes = n_lines * 16;
-            std::vector<unsigned char> joined;
-            if (!part.empty()) {
-                joined.reserve(part.size() + nbytes);
-                joined.insert(joined.end(), part.begin(), part.end());
-                joined.insert(joined.end(), p, p + nbytes);
-                src = joined.data();
-                nbytes = joined.size();
-            }
-            const size_t ntup = nbytes / tbytes;
-            e->lines_received += lines_in;
-            if (ntup) {
-                const size_t old = e->result_words.size();
-                e->result_words.resize(old + ntup);
-                int rc = infer_host(e, src, ntup, e->result_words.data() + old, nullptr);
-                if (rc) { e->result_words.resize(old); return rc; }
-            }
-            std::vector<unsigned char> rest(src + ntup * tbytes, src + nbytes);
-            part.swap(rest);
+            landed = true;
+            e->data_lines_in += n_lines;
+            e->lines_received += n_lines;
+            e->tuples_in += (e->data_lines_in / tcl) - (lines_before / tcl);
             n_lines = 0;
         } else {
             return fail(e, DTE_ERR_STATE, "stream_write while the receiver is idle (write reg 200 first)");
         }
     }
+    if (landed) TRY(sync_sources(e));                     // the caller may reuse its buffer when we return
     return DTE_OK;
+}
+
+int dte_stream_flush(dte_t* e) {
+    if (!e) return DTE_ERR_ARG;
+    if (e->state != dte_engine::ST_DATA) return DTE_OK;
+    return flush_all(e);
 }
 
 int dte_stream_read_packets(dte_t* e, void* cl128, uint8_t* last_flags, size_t max_lines, size_t* got) {
     if (!e || !got || (!cl128 && max_lines)) return DTE_ERR_ARG;
-    // 4 consecutive results per line, word j = tuple 4m+j (ResultsCombiner.sv:132-162)
-    const size_t avail_lines = (e->result_words.size() - e->result_read_pos) / 4;
-    const size_t n = std::min(avail_lines, max_lines);
-    if (n) memcpy(cl128, e->result_words.data() + e->result_read_pos, n * 16);
+    *got = 0;
+    if (!e->ring_cap) return DTE_OK;                      // no run yet
+    if (e->state == dte_engine::ST_DATA) TRY(flush_all(e));
+    // 4 consecutive results per line, word j = tuple 4m+j (ResultsCombiner.sv:132-162).  Wait for the device work
+    // of tuples already written, never for input that has not arrived.
+    const uint64_t submitted = global_prefix(e, false);
+    const uint64_t want_t = std::min<uint64_t>(e->res_read + (uint64_t)max_lines * 4, submitted);
+    for (Dev& d : e->devs) TRY(poll_dev(e, d, 0));
+    if (global_prefix(e, true) < want_t) {
+        if (e->multi() && e->deal) {
+            for (Dev& d : e->devs) TRY(poll_dev(e, d, d.res_enq));
+        } else {
+            TRY(poll_dev(e, e->devs[(size_t)(e->group ? e->pos2dev[0] : 0)], want_t));
+        }
+    }
+    const uint64_t avail = std::min(global_prefix(e, true), want_t);
+    const size_t n = avail > e->res_read ? (size_t)((avail - e->res_read) / 4) : 0;
+    float* out = static_cast<float*>(cl128);
+    uint64_t i = e->res_read;
+    const uint64_t end = e->res_read + (uint64_t)n * 4;
+    const int host_ix = e->multi() ? e->pos2dev[0] : 0;
+    while (i < end) {
+        int dv; uint64_t loc;
+        locate_result(e, i, dv, loc);
+        const Dev& d = e->devs[(size_t)dv];
+        uint64_t run = end - i;
+        if (e->multi() && e->deal) {
+            const uint64_t bt = e->deal_lines / e->g.tuple_cls;
+            run = std::min(run, bt - i % bt);
+        }
+        const size_t pos = (size_t)(loc % d.ring_cap);
+        run = std::min<uint64_t>(run, d.ring_cap - pos);
+        memcpy(out + (i - e->res_read), d.h_ring + pos, (size_t)run * 4);
+        if (dv != host_ix) e->sl3_res_lines += (run + 3) / 4;
+        i += run;
+    }
+    if (e->group) e->sl3_res_lines += n;                  // aggregate mode: every result line came back over the ring
     if (last_flags) {
         // `last` closes a PCIe packet every pcie_out_packet_numcls lines: reg 206[55:48], compared as the
         // 8-bit "minus one" copy (EngineCSR.sv:242, DTInference.sv:632-646,659-663)
         const uint32_t pkt_m1 = (uint32_t)(((e->regs[6] >> 48) & 0xFF) - 1) & 0xFF;
-        for (size_t i = 0; i < n; ++i) {
-            last_flags[i] = e->out_cl_count == pkt_m1;
+        for (size_t k = 0; k < n; ++k) {
+            last_flags[k] = e->out_cl_count == pkt_m1;
             e->out_cl_count = (e->out_cl_count == pkt_m1) ? 0 : ((e->out_cl_count + 1) & 0xFF);
         }
     }
-    e->result_read_pos += n * 4;
+    e->res_read = end;
     e->result_lines_out += n;
     *got = n;
-    if (e->result_read_pos > (1u << 20)) {              // compact the queue now and then
-        e->result_words.erase(e->result_words.begin(), e->result_words.begin() + (ptrdiff_t)e->result_read_pos);
-        e->result_read_pos = 0;
-    }
-    return DTE_OK;
+    bool done;
+    return check_done(e, &done);
 }
 
 int dte_stream_read(dte_t* e, void* cl128, size_t max_lines, size_t* got) {
@@ -738,54 +1181,91 @@ int dte_stream_read(dte_t* e, void* cl128, size_t max_lines, size_t* got) {
 
 int dte_process_done(dte_t* e, int* done) {
     if (!e || !done) return DTE_ERR_ARG;
-    const uint64_t want = e->regs[7] & 0xFFFFFFFFull;                           // reg 207[31:0]
-    const uint64_t produced = e->result_lines_out + (e->result_words.size() - e->result_read_pos) / 4;
-    *done = (want != 0 && produced >= want) ? 1 : 0;
+    bool d = false;
+    TRY(check_done(e, &d));
+    *done = d ? 1 : 0;
     return DTE_OK;
 }
 
 int dte_load_ensemble(dte_t* e, const void* weight_cls, size_t n_weight_cls, const void* findex_cls,
                       size_t n_findex_cls, uint32_t first_tree, uint32_t num_local_trees) {
     if (!e || !weight_cls || !findex_cls || !n_weight_cls || !n_findex_cls) return DTE_ERR_ARG;
-    return load_ensemble(e, static_cast<const unsigned char*>(weight_cls), n_weight_cls,
-                         static_cast<const unsigned char*>(findex_cls), n_findex_cls, first_tree, num_local_trees);
+    const Clock::time_point t0 = Clock::now();
+    Geom g;
+    TRY(decode_geom(e, g));
+    const unsigned char* wl = static_cast<const unsigned char*>(weight_cls);
+    const unsigned char* fl = static_cast<const unsigned char*>(findex_cls);
+    PackedEnsemble pk;
+    if (!e->multi()) {
+        TRY(pack_or_fail(e, g, wl, n_weight_cls, fl, n_findex_cls, first_tree, num_local_trees, pk));
+        TRY(upload_ensemble(e, e->devs[0], pk));
+    } else {
+        TRY(decide_partition(e, g));
+        if (n_weight_cls % g.w_cls) return fail(e, DTE_ERR_ARG, "weights stream: %zu lines is not a multiple of %u lines per tree", n_weight_cls, g.w_cls);
+        const uint32_t T_all = (uint32_t)(n_weight_cls / g.w_cls);
+        if (num_local_trees == 0 && first_tree == 0) num_local_trees = T_all;
+        const uint32_t G = (uint32_t)e->devs.size();
+        if (!e->group) {                             // replicated
+            TRY(pack_or_fail(e, g, wl, n_weight_cls, fl, n_findex_cls, first_tree, num_local_trees, pk));
+            for (Dev& d : e->devs) TRY(upload_ensemble(e, d, pk));
+        } else {
+            // contiguous chunks in ring order (PCIeReceiver.sv:241-264): reg 203's numcls_local_weights if it is a
+            // whole number of trees that covers the ensemble, else an even split
+            const Flags f = decode_flags(e);
+            const bool programmed = (e->regs[3] & 0xFFFF) != 0 && f.chunk_w % g.w_cls == 0 && (f.chunk_w / g.w_cls) * G >= num_local_trees;
+            const uint32_t per = programmed ? (uint32_t)(f.chunk_w / g.w_cls) : (num_local_trees + G - 1) / G;
+            for (uint32_t r = 0; r < G; ++r) {
+                const uint32_t lo = std::min(num_local_trees, r * per), hi = std::min(num_local_trees, (r + 1) * per);
+                if (hi == lo) return fail(e, DTE_ERR_CONFIG, "ring position %u would hold no trees (%u trees over %u devices)", r, num_local_trees, G);
+                TRY(pack_or_fail(e, g, wl, n_weight_cls, fl, n_findex_cls, first_tree + lo, hi - lo, pk));
+                TRY(upload_ensemble(e, e->devs[(size_t)e->pos2dev[r]], pk));
+            }
+        }
+    }
+    e->g = g;
+    e->prog_seen = true; e->prog_open = false;
+    e->t_prog0 = t0; e->t_prog1 = Clock::now();
+    return DTE_OK;
+}
+
+static int infer_device_common(dte_t* e, const void* d_tuples, size_t n, float* d_scores, uint8_t* d_labels, void* cuda_stream,
+                               bool accumulate, const char* what) {
+    TRY(single_only(e, what));
+    Geom g;
+    TRY(decode_geom(e, g));
+    TRY(check_resident(e, g));
+    Dev& d = e->devs[0];
+    d.g.K = g.K; d.g.S = g.S; d.g.missing = g.missing;
+    e->g = g;
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    cudaStream_t st = pick_stream(d, cuda_stream);
+    CUDA_TRY(e, cudaEventRecord(d.ev_t0, st));
+    const char* why = nullptr;
+    cudaError_t rc = launch_walk(d, e->tune, e->forced_variant, d_tuples, n, d_scores, d_labels, st, accumulate, &why);
+    if (rc != cudaSuccess) return fail(e, why ? DTE_ERR_ARG : DTE_ERR_CUDA, "walk kernel launch failed: %s", why ? why : cudaGetErrorString(rc));
+    CUDA_TRY(e, cudaEventRecord(d.ev_t1, st));
+    d.timing_pending = true;
+    e->tuples_in += n;
+    e->tuples_out += n;
+    if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
+    return DTE_OK;
 }
 
 int dte_infer_device(dte_t* e, const void* d_tuples, size_t n, float* d_scores, uint8_t* d_labels, void* cuda_stream) {
     if (!e || (n && (!d_tuples || !d_scores))) return DTE_ERR_ARG;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->s_main;
-    CUDA_TRY(e, cudaEventRecord(e->ev_t0, st));
-    int rc = launch_walk(e, d_tuples, n, d_scores, d_labels, st);
-    if (rc) return rc;
-    CUDA_TRY(e, cudaEventRecord(e->ev_t1, st));
-    e->timing_pending = true;
-    e->tuples_in += n;
-    e->tuples_out += n;
-    if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
-    return DTE_OK;
+    return infer_device_common(e, d_tuples, n, d_scores, d_labels, cuda_stream, false, "dte_infer_device");
 }
 
 int dte_infer_device_accumulate(dte_t* e, const void* d_tuples, size_t n, float* d_scores_accum, void* cuda_stream) {
     if (!e || (n && (!d_tuples || !d_scores_accum))) return DTE_ERR_ARG;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->s_main;
-    CUDA_TRY(e, cudaEventRecord(e->ev_t0, st));
-    int rc = launch_walk(e, d_tuples, n, d_scores_accum, nullptr, st, true);
-    if (rc) return rc;
-    CUDA_TRY(e, cudaEventRecord(e->ev_t1, st));
-    e->timing_pending = true;
-    e->tuples_in += n;
-    e->tuples_out += n;
-    if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
-    return DTE_OK;
+    return infer_device_common(e, d_tuples, n, d_scores_accum, nullptr, cuda_stream, true, "dte_infer_device_accumulate");
 }
 
-// ---- peer-visible buffers (CUDA IPC): the combine target of the fused cross-device reduce ----
+// ---- peer-visible buffers (CUDA IPC): partial-score buffers other processes' combine kernels read ----
 int dte_ipc_alloc(dte_t* e, size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
     if (!e || !d_ptr || !handle_out || !bytes) return DTE_ERR_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
-    CUDA_TRY(e, cudaSetDevice(e->dev));
+    CUDA_TRY(e, cudaSetDevice(e->devs[0].ordinal));
     CUDA_TRY(e, cudaMalloc(d_ptr, bytes));
     cudaIpcMemHandle_t h;
     cudaError_t st = cudaIpcGetMemHandle(&h, *d_ptr);
@@ -800,7 +1280,7 @@ int dte_ipc_alloc(dte_t* e, size_t bytes, void** d_ptr, unsigned char handle_out
 
 int dte_ipc_open(dte_t* e, const unsigned char handle[64], void** d_ptr) {
     if (!e || !handle || !d_ptr) return DTE_ERR_ARG;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
+    CUDA_TRY(e, cudaSetDevice(e->devs[0].ordinal));
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     CUDA_TRY(e, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -809,7 +1289,7 @@ int dte_ipc_open(dte_t* e, const unsigned char handle[64], void** d_ptr) {
 
 int dte_ipc_close(dte_t* e, void* d_ptr, int owner) {
     if (!e || !d_ptr) return DTE_ERR_ARG;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
+    CUDA_TRY(e, cudaSetDevice(e->devs[0].ordinal));
     if (owner) CUDA_TRY(e, cudaFree(d_ptr));
     else CUDA_TRY(e, cudaIpcCloseMemHandle(d_ptr));
     return DTE_OK;
@@ -823,8 +1303,9 @@ int dte_infer_host(dte_t* e, const void* h_tuples, size_t n, float* h_scores, ui
 int dte_labels_device(dte_t* e, const float* d_scores, size_t n, uint8_t* d_labels, void* cuda_stream) {
     if (!e || (n && (!d_scores || !d_labels))) return DTE_ERR_ARG;
     if (!n) return DTE_OK;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->s_main;
+    Dev& d = e->devs[0];
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    cudaStream_t st = pick_stream(d, cuda_stream);
     labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scores, d_labels, n);
     CUDA_TRY(e, cudaGetLastError());
     if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
@@ -834,10 +1315,33 @@ int dte_labels_device(dte_t* e, const float* d_scores, size_t n, uint8_t* d_labe
 int dte_ring_add_device(dte_t* e, const float* d_a, const float* d_b, float* d_out, size_t n, void* cuda_stream) {
     if (!e || (n && (!d_a || !d_b || !d_out))) return DTE_ERR_ARG;
     if (!n) return DTE_OK;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->s_main;
+    Dev& d = e->devs[0];
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    cudaStream_t st = pick_stream(d, cuda_stream);
     ring_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, d_b, d_out, n);
     CUDA_TRY(e, cudaGetLastError());
+    if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
+    return DTE_OK;
+}
+
+int dte_ring_combine_device(dte_t* e, const float* const* d_parts, int n_parts, size_t n, float* d_out, uint8_t* d_labels,
+                            void* cuda_stream) {
+    if (!e || !d_parts || n_parts < 1 || n_parts > kMaxRing || (n && !d_out)) return DTE_ERR_ARG;
+    RingParts parts;
+    for (int g = 0; g < n_parts; ++g) {
+        if (!d_parts[g] || (reinterpret_cast<uintptr_t>(d_parts[g]) & 15u)) return fail(e, DTE_ERR_ARG, "part %d: null or not 16-byte aligned", g);
+        parts.p[g] = d_parts[g];
+    }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15u) || (d_labels && (reinterpret_cast<uintptr_t>(d_labels) & 3u)))
+        return fail(e, DTE_ERR_ARG, "output buffers must be 16-byte (scores) / 4-byte (labels) aligned");
+    if (!n) return DTE_OK;
+    Dev& d = e->devs[0];
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    cudaStream_t st = pick_stream(d, cuda_stream);
+    const unsigned blocks = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)d.sm_count * 8);
+    ring_combine_kernel<<<blocks, 256, 0, st>>>(parts, n_parts, d_out, d_labels, n);
+    CUDA_TRY(e, cudaGetLastError());
+    d.kernel_launches++;
     if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
     return DTE_OK;
 }
@@ -870,54 +1374,53 @@ int dte_csr_from_profile(uint32_t n_trees, uint32_t depth_levels, uint32_t tuple
 
 int dte_get_info(dte_t* e, dte_info* info) {
     if (!e || !info) return DTE_ERR_ARG;
-    if (e->timing_pending) {
-        if (cudaEventSynchronize(e->ev_t1) == cudaSuccess) {
+    Dev& d0 = e->devs[0];
+    if (d0.timing_pending) {
+        cudaSetDevice(d0.ordinal);
+        if (cudaEventSynchronize(d0.ev_t1) == cudaSuccess) {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) {
+            if (cudaEventElapsedTime(&ms, d0.ev_t0, d0.ev_t1) == cudaSuccess) {
+                d0.last_walk_ms = ms;
                 e->last_walk_ms = ms;
-                e->exec_ns += (double)ms * 1e6;
             }
         }
-        e->timing_pending = false;
+        d0.timing_pending = false;
     }
     memset(info, 0, sizeof *info);
-    info->num_trees = e->T;
-    info->num_levels = e->D;
-    info->num_features = e->tuple_cls * 4;
-    info->clusters = e->K;
-    info->trees_per_pu = e->S;
-    info->sm_count = (uint32_t)e->sm_count;
-    info->ensemble_bytes = e->ensemble_bytes;
-    info->kernel_launches = e->kernel_launches;
+    info->num_levels = d0.d_top ? d0.g.D : e->g.D;
+    info->num_features = d0.d_top ? d0.g.F() : e->g.F();
+    info->clusters = e->g.K;
+    info->trees_per_pu = e->g.S;
+    info->sm_count = (uint32_t)d0.sm_count;
+    for (Dev& d : e->devs) {
+        info->ensemble_bytes += d.ensemble_bytes;
+        info->kernel_launches += d.kernel_launches;
+        if (e->group) info->num_trees += d.T;
+    }
+    if (!e->group) info->num_trees = d0.T;
     info->last_walk_ms = e->last_walk_ms;
-    if (e->d_top) {
-        Plan pl = make_plan(e);
+    info->num_devices = (uint32_t)e->devs.size();
+    info->partition = !e->multi() ? 0u : (e->group ? 2u : 1u);
+    info->tuples_in = e->tuples_in;
+    info->tuples_out = e->tuples_out;
+    if (d0.d_top) {
+        Plan pl = make_plan(d0, e->tune, e->forced_variant);
         info->kernel_variant = (uint32_t)pl.variant;
-        info->tuples_per_cta = pl.variant == DTE_KERNEL_GENERIC ? 128u : 32u * (uint32_t)(pl.nwarps / pl.pair);
+        info->tuples_per_cta = pl.variant == KERNEL_GENERIC ? 128u : 32u * (uint32_t)(pl.nwarps / pl.pair);
     }
     return DTE_OK;
 }
 
 int dte_kernel_name(dte_t* e, char* buf, size_t len) {
     if (!e || !buf || !len) return DTE_ERR_ARG;
-    if (!e->d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
-    const Plan pl = make_plan(e);
-    if (pl.variant == DTE_KERNEL_GENERIC) {
-        snprintf(buf, len, "dt_walk_generic<%d>", pl.wide ? 1 : 0);
-    } else {
-        const bool staged = pl.variant == DTE_KERNEL_TILE_STAGED;
-        const int threads = 32 * (pl.nwarps + (staged ? 1 : 0));
-        const int nt_max = pl.pair == 4 ? 672 : (pl.ilp == 8 ? 288 : 416);
-        const int nt = (nt_max > 384 && threads <= 384) ? 384 : nt_max;
-        const bool phased = staged && (e->tune.phased >= 1 || (e->tune.phased == -1 && e->Dtop >= 10)) && e->Dtop >= 3;
-        snprintf(buf, len, "dt_walk_tile<%d, %d, %d, %d, %d> warps=%d stages=%d phased=%d threads=%d smem=%zu",
-                 pl.ilp, pl.pair, staged ? 1 : 0, pl.wide ? 1 : 0, nt, pl.nwarps, pl.nstages, phased ? 1 : 0, threads, pl.smem);
-    }
+    if (!e->devs[0].d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
+    kernel_name(e->devs[0], e->tune, e->forced_variant, buf, len);
     return DTE_OK;
 }
 
 int dte_set_node(dte_t* e, uint32_t node_index) {
-    if (!e || node_index > 19) return DTE_ERR_ARG;             // devices_list has 20 entries (EngineCSR.sv:250-296)
+    if (!e || node_index >= (uint32_t)kMaxRing) return DTE_ERR_ARG;            // devices_list has 20 entries (EngineCSR.sv:250-296)
+    if (e->multi()) return fail(e, DTE_ERR_STATE, "a multi-device handle owns every ring position");
     e->node_index = node_index;
     return DTE_OK;
 }
@@ -932,10 +1435,11 @@ int dte_synth_tuples_device(dte_t* e, void* d_tuples, uint64_t first_tuple, uint
                             uint64_t seed, uint32_t missing_ppm, uint32_t missing_value, void* cuda_stream) {
     if (!e || (n && !d_tuples) || !num_features) return DTE_ERR_ARG;
     if (!n) return DTE_OK;
-    CUDA_TRY(e, cudaSetDevice(e->dev));
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->s_main;
+    Dev& d = e->devs[0];
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    cudaStream_t st = pick_stream(d, cuda_stream);
     const unsigned long long ne = n * num_features;
-    const unsigned blocks = (unsigned)std::min<unsigned long long>((ne + 255) / 256, (unsigned long long)e->sm_count * 32);
+    const unsigned blocks = (unsigned)std::min<unsigned long long>((ne + 255) / 256, (unsigned long long)d.sm_count * 32);
     synth_tuples_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(d_tuples), first_tuple * num_features, ne, seed,
                                                 missing_ppm, missing_value);
     CUDA_TRY(e, cudaGetLastError());

@@ -21,6 +21,10 @@ KERNEL_NAMES = {0: "auto", 1: "generic", 2: "tile", 3: "tile_staged"}
 _u64p = C.POINTER(C.c_uint64)
 ABI = [
     ("dte_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    ("dte_create_multi", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
+    ("dte_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
+    ("dte_stream_flush", C.c_int, [C.c_void_p]),
+    ("dte_ring_combine_device", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("dte_destroy", C.c_int, [C.c_void_p]),
     ("dte_last_error", C.c_char_p, [C.c_void_p]),
     ("dte_softreg_write", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
@@ -55,7 +59,13 @@ class DteInfo(C.Structure):
         ("clusters", C.c_uint32), ("trees_per_pu", C.c_uint32), ("kernel_variant", C.c_uint32),
         ("tuples_per_cta", C.c_uint32), ("sm_count", C.c_uint32), ("ensemble_bytes", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("last_walk_ms", C.c_double),
+        ("num_devices", C.c_uint32), ("partition", C.c_uint32), ("tuples_in", C.c_uint64), ("tuples_out", C.c_uint64),
     ]
+
+
+DTE_OPT_CYCLE_MHZ, DTE_OPT_COMBINE, DTE_OPT_RESULT_QUEUE_LINES, DTE_OPT_CHUNK_TUPLES = 1, 2, 3, 4
+DTE_ERR_BACKPRESSURE = -7
+CUDA_STREAM_LEGACY = 0x1        # cudaStreamLegacy: the handle value that NAMES the legacy default stream
 
 
 class DteError(RuntimeError):
@@ -104,6 +114,16 @@ def csr_from_profile(n_trees, depth_levels, tuple_bytes, clusters=8, missing_val
     return {201 + i: int(regs[i]) for i in range(8)}
 
 
+def _stream(stream):
+    """cudaStream_t for the C ABI.  None -> NULL (the engine's own stream, synchronous call).  An int is a raw
+    cudaStream_t; torch reports the legacy default stream as 0, which the ABI reads as NULL, so 0 is translated to
+    cudaStreamLegacy (0x1) — the call then really runs on, and is ordered with, the caller's default stream."""
+    if stream is None:
+        return None
+    s = int(stream)
+    return C.c_void_p(s if s else CUDA_STREAM_LEGACY)
+
+
 def _ptr(x):
     """Device/host address of a numpy array, a torch tensor, an int, or None."""
     if x is None:
@@ -121,13 +141,22 @@ class Engine:
     """One in-order engine on one GPU (the analogue of one FPGA role)."""
 
     def __init__(self, gpu_ordinal=0):
+        """gpu_ordinal: one CUDA ordinal, or a list of ordinals = one handle driving the whole ring of devices
+        (dte_create_multi; ordinals[d] is device ID d of `devices_list`)."""
         self._lib = load_library()
         self._h = C.c_void_p()
-        rc = self._lib.dte_create(C.byref(self._h), int(gpu_ordinal))
+        if isinstance(gpu_ordinal, (list, tuple)):
+            arr = (C.c_int * len(gpu_ordinal))(*[int(g) for g in gpu_ordinal])
+            rc = self._lib.dte_create_multi(C.byref(self._h), arr, len(gpu_ordinal))
+            self.gpu = int(gpu_ordinal[0]) if gpu_ordinal else 0
+            self.gpus = [int(g) for g in gpu_ordinal]
+        else:
+            rc = self._lib.dte_create(C.byref(self._h), int(gpu_ordinal))
+            self.gpu = int(gpu_ordinal)
+            self.gpus = [self.gpu]
         if rc:
             self._h = C.c_void_p()
             raise DteError(rc, "dte_create failed (no CUDA device? there is no CPU fallback)")
-        self.gpu = int(gpu_ordinal)
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
@@ -195,6 +224,18 @@ class Engine:
         self._check(self._lib.dte_stream_read_packets(self._h, _ptr(out), _ptr(last), int(max_lines), C.byref(got)))
         return out[: got.value], last[: got.value]
 
+    def stream_flush(self):
+        self._check(self._lib.dte_stream_flush(self._h))
+
+    def set_option(self, option, value):
+        self._check(self._lib.dte_set_option(self._h, int(option), int(value)))
+
+    def ring_combine_device(self, d_parts, n, d_out, d_labels=None, stream=None):
+        """out = (((p0 + p1) + p2) + ...) in ring order, one kernel; d_parts may be peer-GPU buffers."""
+        arr = (C.c_void_p * len(d_parts))(*[_ptr(p) for p in d_parts])
+        self._check(self._lib.dte_ring_combine_device(self._h, arr, len(d_parts), int(n), _ptr(d_out), _ptr(d_labels),
+                                                      _stream(stream)))
+
     def process_done(self):
         d = C.c_int()
         self._check(self._lib.dte_process_done(self._h, C.byref(d)))
@@ -210,7 +251,7 @@ class Engine:
     def infer_device(self, d_tuples, n, d_scores, d_labels=None, stream=None):
         """d_* are device pointers (ints) or torch CUDA tensors; stream is a cudaStream_t int (None = engine stream, synchronous)."""
         self._check(self._lib.dte_infer_device(self._h, _ptr(d_tuples), int(n), _ptr(d_scores), _ptr(d_labels),
-                                               _ptr(stream) if stream else None))
+                                               _stream(stream)))
 
     def infer_host(self, tuples, want_labels=True, out_scores=None, out_labels=None):
         """tuples: host array (numpy, or a pinned torch CPU tensor) [n, F] fp32 -> (scores, labels)."""
@@ -228,7 +269,7 @@ class Engine:
     def infer_device_accumulate(self, d_tuples, n, d_scores_accum, stream=None):
         """Walk and ADD the partial scores into d_scores_accum (local or peer-GPU buffer), fused in the kernel."""
         self._check(self._lib.dte_infer_device_accumulate(self._h, _ptr(d_tuples), int(n), _ptr(d_scores_accum),
-                                                          _ptr(stream) if stream else None))
+                                                          _stream(stream)))
 
     def ipc_alloc(self, nbytes):
         """-> (device pointer, 64-byte handle) of a buffer other processes can open."""
@@ -247,16 +288,16 @@ class Engine:
 
     def labels_device(self, d_scores, n, d_labels, stream=None):
         self._check(self._lib.dte_labels_device(self._h, _ptr(d_scores), int(n), _ptr(d_labels),
-                                                _ptr(stream) if stream else None))
+                                                _stream(stream)))
 
     def ring_add_device(self, d_a, d_b, d_out, n, stream=None):
         self._check(self._lib.dte_ring_add_device(self._h, _ptr(d_a), _ptr(d_b), _ptr(d_out), int(n),
-                                                  _ptr(stream) if stream else None))
+                                                  _stream(stream)))
 
     def synth_tuples_device(self, d_tuples, first_tuple, n, num_features, seed, missing_ppm, missing_value, stream=None):
         self._check(self._lib.dte_synth_tuples_device(self._h, _ptr(d_tuples), int(first_tuple), int(n), int(num_features),
                                                       int(seed), int(missing_ppm), int(missing_value),
-                                                      _ptr(stream) if stream else None))
+                                                      _stream(stream)))
 
     def set_node(self, node_index):
         """Entry of devices_list this engine stands for (0 = host node)."""

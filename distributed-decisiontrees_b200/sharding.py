@@ -16,10 +16,16 @@ import numpy as np
 
 
 def ensemble_chunk(n_trees, rank, world):
-    """Contiguous tree range [first, first+count) of device `rank` out of `world`."""
-    per = -(-int(n_trees) // int(world))
-    first = min(int(n_trees), rank * per)
-    return first, max(0, min(int(n_trees), first + per) - first)
+    """Contiguous tree range [first, first+count) of device `rank` out of `world`: chunks of ceil(T/world) trees in
+    ring order, as PCIeReceiver cuts the streams by numcls_local_weights (PCIeReceiver.sv:241-264).  Every device
+    must end up with at least one tree — (first>0, count=0) would read as "all trees" downstream and a rank that
+    raises while its peers wait in a collective hangs the job — so that is refused here, on every rank alike."""
+    n_trees, world = int(n_trees), int(world)
+    per = -(-n_trees // world)
+    if per * (world - 1) >= n_trees:
+        raise ValueError("%d trees cannot be cut into %d non-empty chunks of %d" % (n_trees, world, per))
+    first = rank * per
+    return first, min(n_trees, first + per) - first
 
 
 def data_shard(n_tuples, rank, world):
@@ -75,6 +81,75 @@ def deal_batches(n_lines, batch_cls, world):
         pos += take
         dev = (dev + 1) % world
     return out
+
+
+class RingCombine:
+    """Ensemble-sharded combine in the reference's RING ORDER at the cost of one kernel (one process per GPU).
+
+    Every rank's walk writes its partial scores into a peer-visible buffer (CUDA IPC through libdte.so); rank `dst`
+    (the host node, ring position 0) runs `ring_combine_kernel` over all of them — peers are read over NVLink — and
+    forms score = ((p0 + p1) + p2) + ... with add.rn.ftz.f32, exactly ResultsCombiner.sv:292-311,359-368, then the
+    labels.  torch.distributed only carries the 64-byte handles and the two host barriers of a step."""
+
+    def __init__(self, engine, dist, n):
+        import torch
+        self.engine, self.dist, self.n = engine, dist, int(n)
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        err, handle = None, None
+        try:
+            self.ptr, handle = engine.ipc_alloc(4 * self.n)
+        except Exception as ex:                          # noqa: BLE001
+            self.ptr, err = None, "rank %d: %s" % (self.rank, ex)
+        boxes = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(boxes, (handle, err))
+        else:
+            boxes = [(handle, err)]
+        err = next((b[1] for b in boxes if b[1]), None)
+        self.ptrs = None
+        if err is None and self.rank == 0:
+            try:
+                self.ptrs = [self.ptr] + [engine.ipc_open(boxes[r][0]) for r in range(1, self.world)]
+            except Exception as ex:                      # noqa: BLE001
+                err = "rank 0: %s" % ex
+        if self.world > 1:
+            flags = [None] * self.world
+            dist.all_gather_object(flags, err)
+            err = next((f for f in flags if f), None)
+        if err:
+            self.close()
+            raise RuntimeError("ring combine unavailable (%s)" % err)
+        self.part = torch.as_tensor(_CudaArray(self.ptr, self.n), device="cuda")
+
+    def step(self, d_tuples, n, stream, d_out=None, d_labels=None):
+        """walk -> barrier -> (rank 0) ONE combine kernel -> barrier.  Rank 0 gets scores in d_out, labels in d_labels."""
+        import torch
+        self.engine.infer_device(d_tuples, n, self.ptr, None, stream=stream)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        if self.rank == 0:
+            self.engine.ring_combine_device(self.ptrs, n, d_out, d_labels, stream=stream)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()                          # the peers may now overwrite their partials
+
+    def close(self):
+        self.part = None
+        if getattr(self, "ptrs", None):
+            for p in self.ptrs[1:]:
+                try:
+                    self.engine.ipc_close(p, False)
+                except Exception:                        # noqa: BLE001
+                    pass
+            self.ptrs = None
+        if getattr(self, "ptr", None) is not None:
+            try:
+                self.engine.ipc_close(self.ptr, True)
+            except Exception:                            # noqa: BLE001
+                pass
+            self.ptr = None
 
 
 class _CudaArray:
@@ -137,7 +212,7 @@ class FusedCombine:
         torch.cuda.synchronize()
         if self.dist is not None and self.dist.get_world_size() > 1:
             self.dist.barrier()
-        self.engine.infer_device_accumulate(d_tuples, n, self.ptr, stream=stream)
+        self.engine.infer_device_accumulate(d_tuples, n, self.ptr, stream=stream)     # stream: torch handle (0 = legacy default)
         torch.cuda.synchronize()
         if self.dist is not None and self.dist.get_world_size() > 1:
             self.dist.barrier()

@@ -33,7 +33,8 @@ typedef enum {
     DTE_ERR_CONFIG = -3,       /* CSR contents inconsistent (e.g. line counts too small for D) */
     DTE_ERR_UNSUPPORTED = -4,  /* ensemble uses a feature outside the contract (bit 14, index >= F) */
     DTE_ERR_CUDA = -5,         /* CUDA runtime error or no device */
-    DTE_ERR_NOMEM = -6
+    DTE_ERR_NOMEM = -6,
+    DTE_ERR_BACKPRESSURE = -7  /* result queue full: read result lines, then repeat the write (pcie_full_out) */
 } dte_status;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -41,6 +42,24 @@ typedef enum {
  * (rtl/SimpleRole.sv:29-63).  The loaded ensemble survives any number of `start`s, as the PU
  * tree memories survive everything but a hardware reset (rtl/DTEngine/core/DTPU.sv:307-319). */
 int dte_create(dte_t** engine, int gpu_ordinal);
+/* One engine driving SEVERAL devices from one process: the whole ring of FPGAs behind the host node
+ * (rtl/DTEngine/EngineCSR.sv:194-216,250-296; PCIeReceiver.sv:241-264,298-307; InputDistributor.sv:199-204;
+ * ResultsCombiner.sv:292-311,359-391).  gpu_ordinals[d] is the CUDA device that device ID d of `devices_list`
+ * (registers 208-210, 5 bits per byte lane) refers to; ring position i is served by device ID
+ * devices_list[i] (identity when the registers are left at 0).  Peer access is enabled between all devices.
+ * The handle then behaves like the host node's PCIe endpoint: ONE register file, ONE input line stream, ONE
+ * result stream; registers 201/203 select the partition exactly as on the Catapult ring:
+ *   broadcast_trees=1, broadcast_data=0 : every device holds the whole ensemble, data lines are dealt in batches of
+ *       core_data_batch_cls lines (reg 201[63:32]) round-robin over numDevs (reg 203[39:32]) devices; results are
+ *       merged back in GLOBAL tuple order (the reference's arbitration order is timing-dependent,
+ *       ResultsCombiner.sv:346-353; tuple order is the deterministic choice) — BASELINE configs[4].
+ *   broadcast_trees=0, broadcast_data=1, aggreg_enabled=1 : the tree streams are cut into per-device chunks of
+ *       numcls_local_weights / numcls_local_findexes lines (reg 203), every device walks every tuple (each device
+ *       uploads 1/numDevs of the lines over its own PCIe link and the rest crosses NVLink peer-to-peer), and the
+ *       partial scores are summed IN RING ORDER, host first, by one kernel on the host device that reads its
+ *       peers over NVLink — bit-exact with the reference's ring of adders — BASELINE configs[3].
+ * Any other combination on a multi-device handle is refused with DTE_ERR_CONFIG at `start`. */
+int dte_create_multi(dte_t** engine, const int* gpu_ordinals, int n_gpus);
 int dte_destroy(dte_t* engine);
 /* Last error text for this handle (never NULL; valid until the next call on the handle). */
 const char* dte_last_error(const dte_t* engine);
@@ -72,16 +91,23 @@ int dte_set_node(dte_t* engine, uint32_t node_index);
  *   tuple CLs only and the resident ensemble is reused.  May be called with any chunking. */
 int dte_stream_write(dte_t* engine, const void* cl128, size_t n_lines);
 /* Replaces the PCIe DMA output stream written by rtl/DTEngine/ResultsCombiner.sv:132-162,426-454:
- * result CLs, 4 fp32 scores each, tuple order.  Copies up to max_lines finished lines, never
- * blocks; *got = lines copied.  A trailing group of fewer than 4 results stays inside the engine
- * exactly as in the RTL (ResultsCombiner.sv:153-155). */
+ * result CLs, 4 fp32 scores each, tuple order.  Copies up to max_lines result lines; it waits for the device
+ * work of tuples ALREADY WRITTEN (it never waits for input that has not arrived), *got = lines copied.  A trailing
+ * group of fewer than 4 results stays inside the engine exactly as in the RTL (ResultsCombiner.sv:153-155).
+ * dte_stream_write is asynchronous: it returns once the lines have left the caller's buffer (H2D enqueued and
+ * complete); walk and D2H of earlier lines overlap later writes.  Results queue in a bounded pinned ring sized
+ * from reg 207 (total_results_numcls): a write that would overflow it returns DTE_ERR_BACKPRESSURE and consumes
+ * nothing (the RTL raises pcie_full_out, PCIeReceiver.sv:126). */
 int dte_stream_read(dte_t* engine, void* cl128, size_t max_lines, size_t* got);
 /* Same, also returning the PCIe packet framing: last_flags[i] = 1 when line i closes a packet of
  * pcie_out_packet_numcls lines (reg 206[55:48]; `last` of pcie_packet_out, DTInference.sv:659-663). */
 int dte_stream_read_packets(dte_t* engine, void* cl128, uint8_t* last_flags, size_t max_lines, size_t* got);
 /* 1 when as many result lines as reg 207[31:0] asks for have been produced
- * (process_done, rtl/DTEngine/DTInference.sv:633-663). */
+ * (process_done, rtl/DTEngine/DTInference.sv:633-663); the receiver then returns to IDLE
+ * (PCIeReceiver.sv:289-292) until the next `start`. */
 int dte_process_done(dte_t* engine, int* done);
+/* Submit whatever whole tuples are waiting in a partly filled landing buffer (no blocking). */
+int dte_stream_flush(dte_t* engine);
 
 /* ---- fast paths (same engine, same kernels, no line framing) -------------------------------- */
 /* Program the ensemble from the two tree streams held in host memory, using the geometry already
@@ -95,7 +121,12 @@ int dte_load_ensemble(dte_t* engine, const void* weight_cls, size_t n_weight_cls
 
 /* Scores (and optionally labels = score > 0.0f, may be NULL) for n tuples that already sit in
  * device memory as n*tuple_numcls CLs (row-major fp32 [n][F]).  Asynchronous on `cuda_stream`
- * (a cudaStream_t passed as void*; NULL = the engine's own stream, then the call synchronises). */
+ * (a cudaStream_t passed as void*; NULL = the engine's own stream, then the call synchronises).
+ * The CUDA legacy default stream has the handle value 0 in the runtime API; pass DTE_STREAM_LEGACY
+ * (= cudaStreamLegacy) or DTE_STREAM_PER_THREAD (= cudaStreamPerThread) to name it explicitly.
+ * Single-device handles only (a multi-device handle takes host buffers: dte_infer_host / the line stream). */
+#define DTE_STREAM_LEGACY ((void*)0x1)
+#define DTE_STREAM_PER_THREAD ((void*)0x2)
 int dte_infer_device(dte_t* engine, const void* d_tuples, size_t n, float* d_scores,
                      uint8_t* d_labels, void* cuda_stream);
 
@@ -124,6 +155,25 @@ int dte_labels_device(dte_t* engine, const float* d_scores, size_t n, uint8_t* d
  * ResultsCombiner ring (ResultsCombiner.sv:292-311).  out may alias a or b. */
 int dte_ring_add_device(dte_t* engine, const float* d_a, const float* d_b, float* d_out, size_t n, void* cuda_stream);
 
+/* The WHOLE ring in one kernel: out[i] = (((p[0][i] + p[1][i]) + p[2][i]) + ...) + p[n_parts-1][i], host first, every
+ * add = add.rn.ftz.f32 — bit-exact with the reference's aggregate mode (ResultsCombiner.sv:292-311,359-368), and
+ * labels[i] = out[i] > 0 (NULL to skip).  The part pointers may be buffers of PEER GPUs (dte_ipc_open, or peer access
+ * inside one process): the kernel reads them over NVLink, so the cross-device combine costs one launch and no
+ * collective.  n_parts <= 20 (devices_list); pointers 16-byte aligned. */
+int dte_ring_combine_device(dte_t* engine, const float* const* d_parts, int n_parts, size_t n, float* d_out,
+                            uint8_t* d_labels, void* cuda_stream);
+
+/* ---- options -------------------------------------------------------------------------------- */
+typedef enum {
+    DTE_OPT_CYCLE_MHZ = 1,        /* registers 222/223: 0 (default) = nanoseconds; f > 0 = cycles of an f-MHz clock
+                                     (150 = the Catapult role clock assumed by profiler/profiler.cpp:33) */
+    DTE_OPT_COMBINE = 2,          /* multi-device aggregate mode: 0 (default) = ring-order peer-read kernel (bit-exact),
+                                     1 = one ncclReduce(SUM) to the host device (order free: 1e-5 relative) */
+    DTE_OPT_RESULT_QUEUE_LINES = 3, /* capacity of the result queue in 128-bit lines (0 = derive from reg 207) */
+    DTE_OPT_CHUNK_TUPLES = 4      /* tuples per landing buffer of the H2D | walk | D2H pipeline (0 = 64 MiB worth) */
+} dte_option;
+int dte_set_option(dte_t* engine, int option, uint64_t value);
+
 /* ---- parameters in the profiler's vocabulary ------------------------------------------------ */
 /* The reference's only C++ parameter surface is profiler/profiler.cpp:31-41 (N_trees, Depth_tree,
  * Size_tuple_Bytes).  This derives every register value of one device from those three numbers
@@ -145,8 +195,12 @@ typedef struct {
     uint32_t tuples_per_cta;   /* tuple tile held in shared memory by one CTA */
     uint32_t sm_count;
     uint64_t ensemble_bytes;   /* device bytes of the repacked ensemble */
-    uint64_t kernel_launches;  /* walk-kernel launches since create */
+    uint64_t kernel_launches;  /* walk-kernel launches since create (all devices) */
     double   last_walk_ms;     /* device time of the most recent walk launch(es) of one infer call */
+    uint32_t num_devices;      /* devices behind this handle */
+    uint32_t partition;        /* 0 single device, 1 data-sharded (trees replicated), 2 ensemble-sharded (ring combine) */
+    uint64_t tuples_in;        /* whole tuples received since create */
+    uint64_t tuples_out;       /* results produced since create */
 } dte_info;
 int dte_get_info(dte_t* engine, dte_info* info);
 

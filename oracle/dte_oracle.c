@@ -5,7 +5,10 @@
  *
  * Every function cites the reference lines it restates (paths relative to /root/reference).
  */
+#define _GNU_SOURCE
 #include "dte_oracle.h"
+#include <sched.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -184,8 +187,39 @@ static uint32_t score_one(const dteo_cfg* c, const uint32_t* W, const uint16_t* 
     return literal_adder ? fp34_unwrap(tot_b) : tot_a;
 }
 
-int dteo_max_threads(void) {
+int dteo_online_cpus(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+/* CPUs this process may actually use: online CPUs, cut by the affinity mask, cut by the cgroup CPU quota
+   (cgroup v2 cpu.max "quota period", v1 cpu.cfs_quota_us / cpu.cfs_period_us).  The quota matters: a 1-GPU
+   lease on a 128-thread host can be capped at ~11 cores, and 128 busy threads then only thrash. */
+int dteo_max_threads(void) {
+    long n = dteo_online_cpus();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+        int c = CPU_COUNT(&set);
+        if (c > 0 && c < n) n = c;
+    }
+    double quota = -1, period = -1;
+    FILE* fh = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (fh) {
+        char q[64];
+        if (fscanf(fh, "%63s %lf", q, &period) == 2 && q[0] != 'm') quota = atof(q);
+        fclose(fh);
+    } else {
+        FILE* fq = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+        FILE* fp = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+        if (fq && fp && fscanf(fq, "%lf", &quota) == 1 && fscanf(fp, "%lf", &period) == 1) { /* both read */ }
+        if (fq) fclose(fq);
+        if (fp) fclose(fp);
+    }
+    if (quota > 0 && period > 0) {
+        long c = (long)((quota + period - 1) / period);
+        if (c < 1) c = 1;
+        if (c < n) n = c;
+    }
     return n > 0 ? (int)n : 1;
 }
 
@@ -232,6 +266,92 @@ int dteo_scores(const dteo_cfg* c, const void* weights_cls, const void* findex_c
         score_job j = {c, W, FI, X, scores, lo, hi, F, literal_adder};
         jobs[k] = j;
         if (pthread_create(&th[k], NULL, score_worker, &jobs[k])) { score_worker(&jobs[k]); th[k] = 0; }
+    }
+    for (int k = 0; k < threads; ++k) if (th[k]) pthread_join(th[k], NULL);
+    free(th); free(jobs);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Tree-blocked evaluation order — the SAME arithmetic as score_one() (model-A adder), the same   */
+/* per-tuple summation order, but the loops are interchanged so that one tree8 group is walked by */
+/* a block of tuples before the next group is touched: the 8 trees (8 x 10*2^D bytes) stay in     */
+/* cache instead of the whole ensemble streaming past every tuple.  For a fixed tuple the         */
+/* operation sequence is unchanged: per cluster j, slots s ascending: acc_j = tree8(...) + acc_j  */
+/* (FPAggregator.v:79-131); then tot = acc_j + tot, j ascending (Core.sv:486-542).  This is the   */
+/* loop timed as the CPU baseline; tests assert it is bit-identical to dteo_scores().             */
+/* ------------------------------------------------------------------------------------------ */
+#define DTEO_BLOCK 64
+static void score_block(const dteo_cfg* c, const uint32_t* W, const uint16_t* FI, const uint32_t* X, size_t F,
+                        size_t nb, uint32_t* out) {
+    const uint32_t K = c->clusters, S = c->trees_per_pu, T = c->num_trees;
+    const size_t wstride = (size_t)c->tree_w_cls * 4, fstride = (size_t)c->tree_f_cls * 8;
+    uint32_t acc[DTEO_BLOCK][8];
+    uint32_t leaf[DTEO_BLOCK][8];
+    memset(acc, 0, sizeof acc);
+    for (uint32_t s = 0; s < S; ++s) {
+        for (uint32_t j = 0; j < K; ++j) {
+            const uint64_t g = (uint64_t)s * K + j;
+            for (uint32_t p = 0; p < 8; ++p) {
+                const uint64_t t = g * 8 + p;
+                if (t < T) {
+                    const uint32_t* w = W + t * wstride;
+                    const uint16_t* fi = FI + t * fstride;
+                    for (size_t b = 0; b < nb; ++b) leaf[b][p] = dteo_leaf(c, w, fi, X + b * F);
+                } else {
+                    for (size_t b = 0; b < nb; ++b) leaf[b][p] = 0u;
+                }
+            }
+            for (size_t b = 0; b < nb; ++b) acc[b][j] = dteo_fpadd(tree8_a(leaf[b]), acc[b][j]);
+        }
+    }
+    for (size_t b = 0; b < nb; ++b) {
+        uint32_t tot = 0;
+        for (uint32_t j = 0; j < K; ++j) tot = dteo_fpadd(acc[b][j], tot);
+        out[b] = tot;
+    }
+}
+
+static void* blocked_worker(void* arg) {
+    score_job* j = (score_job*)arg;
+    for (size_t i = j->lo; i < j->hi; i += DTEO_BLOCK) {
+        size_t nb = j->hi - i < DTEO_BLOCK ? j->hi - i : DTEO_BLOCK;
+        score_block(j->c, j->W, j->FI, j->X + i * j->F, j->F, nb, j->scores + i);
+    }
+    return NULL;
+}
+
+int dteo_scores_blocked(const dteo_cfg* c, const void* weights_cls, const void* findex_cls,
+                        const void* tuple_cls, size_t n, uint32_t* scores, int threads) {
+    if (check_cfg(c)) return -1;
+    const uint32_t* W = (const uint32_t*)weights_cls;
+    const uint16_t* FI = (const uint16_t*)findex_cls;
+    const uint32_t* X = (const uint32_t*)tuple_cls;
+    const size_t F = (size_t)c->tuple_cls * 4;
+    for (uint32_t t = 0; t < c->num_trees; ++t) {
+        const uint16_t* fi = FI + (size_t)t * c->tree_f_cls * 8;
+        for (uint32_t i = 0; i + 1 < (1u << c->num_levels); ++i) {
+            if ((fi[i] & 0x7FFu) >= F) return -3;
+            if (fi[i] & 0x4000u) return -4;
+        }
+    }
+    if (threads < 1) threads = 1;
+    size_t nblocks = (n + DTEO_BLOCK - 1) / DTEO_BLOCK;
+    if ((size_t)threads > nblocks) threads = nblocks ? (int)nblocks : 1;
+    if (threads == 1) {
+        score_job j = {c, W, FI, X, scores, 0, n, F, 0};
+        blocked_worker(&j);
+        return 0;
+    }
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+    score_job* jobs = (score_job*)malloc(sizeof(score_job) * (size_t)threads);
+    if (!th || !jobs) { free(th); free(jobs); return -5; }
+    for (int k = 0; k < threads; ++k) {              /* whole blocks per thread, contiguous */
+        size_t lo = nblocks * (size_t)k / (size_t)threads * DTEO_BLOCK, hi = nblocks * (size_t)(k + 1) / (size_t)threads * DTEO_BLOCK;
+        if (hi > n) hi = n;
+        score_job j = {c, W, FI, X, scores, lo, hi, F, 0};
+        jobs[k] = j;
+        if (pthread_create(&th[k], NULL, blocked_worker, &jobs[k])) { blocked_worker(&jobs[k]); th[k] = 0; }
     }
     for (int k = 0; k < threads; ++k) if (th[k]) pthread_join(th[k], NULL);
     free(th); free(jobs);
@@ -339,6 +459,20 @@ void dteo_ring_combine(const uint32_t* const* partials, int G, size_t n, uint32_
         for (int g = 1; g < G; ++g) acc = dteo_fpadd(partials[g][i], acc);
         out[i] = acc;
     }
+}
+
+/* ResultsCombiner line packing (ResultsCombiner.sv:132-162): local results fill words curr_word = 0..3 of a
+   128-bit line; the line is emitted when the 4th word is written; fewer than 4 trailing results never leave. */
+size_t dteo_result_lines(const uint32_t* scores, size_t n, uint32_t* lines) {
+    uint32_t line[4] = {0, 0, 0, 0};
+    unsigned curr_word = 0;
+    size_t out = 0;
+    for (size_t i = 0; i < n; ++i) {
+        line[curr_word] = scores[i];
+        if (curr_word == 3) { memcpy(lines + 4 * out, line, 16); ++out; }
+        curr_word = (curr_word + 1) & 3;
+    }
+    return out;
 }
 
 void dteo_labels(const uint32_t* scores, size_t n, uint8_t* labels) {

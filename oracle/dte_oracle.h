@@ -73,7 +73,18 @@ void dteo_ring_combine(const uint32_t* const* partials, int G, size_t n, uint32_
 /* --- build-defined label rule (the reference has no labels): label = score > 0.0f --- */
 void dteo_labels(const uint32_t* scores, size_t n, uint8_t* labels);
 
-/* --- online host cores --- */
+/* --- the same scores with the loops interchanged (a block of tuples walks one tree8 group at a time, so the trees stay
+ *     in cache); identical arithmetic and per-tuple summation order — bit-identical to dteo_scores(literal_adder=0).
+ *     This is the loop bench.py times as the CPU baseline. --- */
+int dteo_scores_blocked(const dteo_cfg* c, const void* weights_cls, const void* findex_cls,
+                        const void* tuple_cls, size_t n, uint32_t* scores, int threads);
+
+/* --- ResultsCombiner line packing: 4 results per 128-bit line, a trailing group of < 4 is not emitted
+ *     (ResultsCombiner.sv:132-162).  lines must hold 4*(n/4) words; returns the number of lines. --- */
+size_t dteo_result_lines(const uint32_t* scores, size_t n, uint32_t* lines);
+
+/* --- host cores: online, and usable (online ∩ affinity mask ∩ cgroup CPU quota) --- */
+int dteo_online_cpus(void);
 int dteo_max_threads(void);
 
 #ifdef __cplusplus

@@ -53,6 +53,11 @@ def lib():
         L.dteo_labels.restype = None
         L.dteo_labels.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.dteo_max_threads.restype = C.c_int
+        L.dteo_online_cpus.restype = C.c_int
+        L.dteo_scores_blocked.restype = C.c_int
+        L.dteo_scores_blocked.argtypes = [C.POINTER(Cfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        L.dteo_result_lines.restype = C.c_size_t
+        L.dteo_result_lines.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -85,6 +90,30 @@ def scores(cfg, weights_cls, findex_cls, tuples, literal_adder=False, threads=1)
     if rc:
         raise RuntimeError("dteo_scores failed: %d" % rc)
     return out
+
+
+def scores_blocked(cfg, weights_cls, findex_cls, tuples, threads=1):
+    """Same words as scores(), computed tree-group by tree-group over blocks of tuples (cache-friendly)."""
+    w = np.ascontiguousarray(weights_cls)
+    f = np.ascontiguousarray(findex_cls)
+    t = np.ascontiguousarray(tuples)
+    n = t.shape[0]
+    out = np.empty(n, dtype=np.uint32)
+    rc = lib().dteo_scores_blocked(C.byref(cfg), w.ctypes.data, f.ctypes.data, t.ctypes.data, n, out.ctypes.data, int(threads))
+    if rc:
+        raise RuntimeError("dteo_scores_blocked failed: %d" % rc)
+    return out
+
+
+def result_lines(score_words):
+    s = np.ascontiguousarray(score_words, dtype=np.uint32)
+    out = np.empty((s.size // 4, 4), dtype=np.uint32)
+    n = lib().dteo_result_lines(s.ctypes.data, s.size, out.ctypes.data)
+    return out[:n]
+
+
+def online_cpus():
+    return int(lib().dteo_online_cpus())
 
 
 def scores_literal(cfg, weights_cls, findex_cls, tuples):

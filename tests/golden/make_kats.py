@@ -156,6 +156,50 @@ cases.append(dict(
     expect=[0],
 ))
 
+# 12 -- trees and tuples that span SEVERAL 128-bit lines, with line padding between trees.
+#       D=3: W = 15 words -> 4 lines (1 pad word), FI = 7 entries -> 1 line (1 pad entry); F = 8 -> 2 lines per tuple.
+#       Word i of a line is bits [32i+31:32i] (PipelinedMUX.sv:63-65); a tree's arrays start on a line boundary
+#       (InputDistributor.sv:276-296 counts whole lines per tree); feature f lives in line f/4, word f%4 (DTPU.sv:628).
+def const_tree(D, leaf):
+    return {"W": [f(0.5)] * ((1 << D) - 1) + [leaf] * (1 << D), "FI": [0] * ((1 << D) - 1)}
+
+tree_a = {"W": [f(0.5)] * 7 + [f(2.0 ** i) for i in range(8)], "FI": [0, 1, 2, 3, 4, 5, 6]}            # node i tests feature i
+tree_b = {"W": [f(0.5)] * 7 + [f(2.0 ** (8 + i)) for i in range(8)], "FI": [6, 5, 4, 3, 2, 1, 0]}      # node i tests feature 6-i
+lo, hi = f(0.1), f(0.9)
+cases.append(dict(
+    name="multi_line_trees_and_tuples", D=3, K=1, S=1, missing=MISS, F=8,
+    why="t0 all-left: A 0->1->3->leaf W[7]=1, B 0->1->3->W[7]=256: 257.  t1 x=[R,L,R,L,L,R,L,-]: A 0-R->2 (x2=R)->6 (x6=L)-> "
+        "leaf W[13]=64 (4th line of W); B node0 tests x6=L->1, node1 tests x5=R->4, node4 tests x2=R-> leaf W[10]=2^11: 2112 "
+        "(features 5 and 6 sit in the tuple's SECOND line)",
+    trees=[tree_a, tree_b] + [const_tree(3, 0)] * 6,
+    tuples=[[lo] * 8, [hi, lo, hi, lo, lo, hi, lo, 0]],
+    expect=[f(257.0), f(2112.0)],
+))
+
+# 13 -- R10 stride decision: a PU's second tree starts TRUE-lines-per-tree after the first (the RTL wires the minus-one
+#       copies into the stride, DTInference.sv:505-506 vs InputDistributor.sv:284-285 / DTPU.sv:522-523).
+#       K=1, S=2: trees 0 and 8 share PU 0 (slot 0 and slot 1).  D=4: W = 31 words -> 8 lines, FI = 15 -> 2 lines.
+def tree_d4(first_exp):
+    return {"W": [f(0.5)] * 15 + [f(2.0 ** (first_exp + i)) for i in range(16)], "FI": [i % 4 for i in range(15)]}
+
+cases.append(dict(
+    name="second_slot_uses_true_line_stride", D=4, K=1, S=2, missing=MISS, F=4,
+    why="x=[R,L,R,L]: 0-R->2 (f2=R)->6 (f2=R)->14 (f2=R)-> leaf W[30]: tree 0 gives 2^15, tree 8 gives 2^31; slot 0 sum 2^15, "
+        "then acc = 2^31 + 2^15 (exact).  With a 7-line stride tree 8 would be read 4 words early (leaf 2^27).",
+    trees=[tree_d4(0)] + [const_tree(4, 0)] * 7 + [tree_d4(16)],
+    tuples=[[hi, lo, hi, lo]],
+    expect=[f(2147516416.0)],
+))
+
+# result packing (ResultsCombiner.sv:132-162): 4 consecutive results per line, word j = tuple 4m+j; a trailing group
+# of fewer than 4 results is never emitted (:153-155, curr_word only wraps on the 4th fill)
+lines_kat = dict(
+    name="result_lines_flush_on_fourth",
+    why="6 results -> ONE line {r0,r1,r2,r3}; r4, r5 stay in the line register",
+    scores=[f(1.0), f(2.0), f(3.0), f(4.0), f(5.0), f(6.0)],
+    expect_lines=[[f(1.0), f(2.0), f(3.0), f(4.0)]],
+)
+
 # ring combine (ResultsCombiner.sv:292-311,359-368): ((p_host + p_1) + p_2)
 ring = dict(
     name="ring_order_3dev",
@@ -164,7 +208,7 @@ ring = dict(
     expect=[0, f(6.0)],
 )
 
-out = {"about": "hand-derived KATs; see make_kats.py for the derivations", "cases": cases, "ring": [ring]}
+out = {"about": "hand-derived KATs; see make_kats.py for the derivations", "cases": cases, "ring": [ring], "lines": [lines_kat]}
 with open(os.path.join(HERE, "kats.json"), "w") as fh:
     json.dump(out, fh, indent=1)
 print("wrote", len(cases), "cases")

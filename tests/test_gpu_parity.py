@@ -11,7 +11,7 @@ import pytest
 
 import ddt_b200 as ddt
 from ddt_b200 import engine as E
-from helpers import kat_arrays, oracle_cfg, geometry_regs, L
+from helpers import kat_arrays, oracle_cfg, geometry_regs, multi_node_regs as _multi_node_regs, L
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -170,11 +170,16 @@ def test_register_and_line_stream_interface():
             out.append(e.stream_read(97))
         out.append(e.stream_read(1 << 20))
         got = np.concatenate(out)
-        assert e.softreg_read(220) == 3                       # RECEIVE_DATA
         assert e.softreg_read(221) == stream.shape[0]
         assert got.shape == (n // 4, 4)                       # the last 3 results never flush (ResultsCombiner.sv:153-155)
         assert (got.reshape(-1).view(np.uint32) == want[: (n // 4) * 4].view(np.uint32)).all()
-        assert e.process_done() == (regs[207] & 0xFFFFFFFF == n // 4)
+        assert regs[207] & 0xFFFFFFFF == n // 4 and e.process_done()
+        assert e.softreg_read(220) == 0                       # process_done -> the receiver is IDLE again (PCIeReceiver.sv:289-292)
+        exec_ns = e.softreg_read(223)
+        assert exec_ns > 0 and e.softreg_read(223) == exec_ns     # execCycles stops at process_done (DTInference.sv:330-345)
+        assert e.softreg_read(222) > 0                        # progCycles: the tree stream took time
+        with pytest.raises(E.DteError):
+            e.stream_write(stream[:4])                         # idle until the next start
         # "load the model once, then any number of start + data runs": data-only restart
         e.softreg_write(201, (regs[201] & ~0x2) | 0x1)        # host_node=0, data_distributed=1
         e.start()
@@ -182,7 +187,16 @@ def test_register_and_line_stream_interface():
         e.stream_write(x[:64].view(np.uint8).reshape(-1, 16))
         again = e.stream_read(100)
         assert (again.reshape(-1).view(np.uint32) == want[:64].view(np.uint32)).all()
-        assert e.softreg_read(223) > 0 and e.softreg_read(125) == T
+        assert e.softreg_read(223) > 0 and e.info()["num_trees"] == T
+        # appStatus[2] = {data_lines, prog_lines} (DTInference.sv:369): 64 tuples x 8 lines, no tree lines in this run
+        assert e.softreg_read(123) == (64 * (F // 4)) << 32
+        # appStatus[1] = {num_out_tuples, cluster_tree_res_out[0]}: K = 2 -> cluster 0 serves every 4th tuple, S = 1
+        a1 = e.softreg_read(122)
+        assert a1 >> 32 == 64 and (a1 & 0xFFFFFFFF) == -(-1003 * K // 8) + 64 * K // 8
+        e.set_option(E.DTE_OPT_CYCLE_MHZ, 150)                # registers 222/223 as 150 MHz cycles
+        ns_view = e.softreg_read(223)
+        e.set_option(E.DTE_OPT_CYCLE_MHZ, 0)
+        assert 0 < ns_view < e.softreg_read(223)
         # packet framing of the output stream: `last` every pcie_out_packet_numcls lines (reg 206[55:48] = 8)
         e.start()
         e.stream_write(x[:400].view(np.uint8).reshape(-1, 16))
@@ -324,23 +338,6 @@ def test_cpp_host_program_matches_python_path():
         wl, fl = L.pack_streams(W, FI, D)
         want = O.scores(oracle_cfg(D, K, 1, L.MISSING_DEFAULT, F, T), wl, fl, x, threads=8)
         assert r["results"] == n and r["score_words_sum"] == int(want.astype(np.uint64).sum()), (mode, r)
-
-
-def _multi_node_regs(T, D, F, K, n, ndev, mode, batch_tuples=2):
-    """Register values of a multi-device run as a Catapult host would write them (EngineCSR.sv:194-216)."""
-    w_cls, f_cls = L.tree_cls(D)
-    per = -(-T // ndev)
-    regs = E.csr_from_profile(T, D, 4 * F, K, L.MISSING_DEFAULT, n)
-    flags = 0x2 | 0x20 | 0x40                       # host_node | multiple_nodes | pcie_receiver_enabled
-    if mode == "ensemble":
-        flags |= 0x4 | 0x10                         # broadcast_data | aggreg_enabled
-        S = -(-per // (8 * K))
-        regs[205] = (regs[205] & ~(0xFF << 36)) | (S << 36)
-    else:
-        flags |= 0x8                                # broadcast_trees
-    regs[201] = flags | ((batch_tuples * (F // 4)) << 32)
-    regs[203] = ((per * w_cls - 1) & 0xFFFF) | ((per * f_cls) << 16) | (ndev << 32)
-    return regs
 
 
 @pytest.mark.parametrize("mode", ["ensemble", "data"])

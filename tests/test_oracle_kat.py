@@ -14,13 +14,12 @@ def _case_ids(k):
 
 
 def test_kats_present(kats):
-    assert len(kats["cases"]) >= 12 and len(kats["ring"]) >= 1
+    assert len(kats["cases"]) >= 15 and len(kats["ring"]) >= 1 and len(kats["lines"]) >= 1
 
 
-@pytest.mark.parametrize("idx", range(13))
+@pytest.mark.parametrize("idx", range(15))
 def test_oracle_reproduces_kat(kats, idx):
-    if idx >= len(kats["cases"]):
-        pytest.skip("no such case")
+    assert len(kats["cases"]) == 15, "update the parametrisation"
     c = kats["cases"][idx]
     W, FI, x = kat_arrays(c)
     wl, fl = L.pack_streams(W, FI, c["D"])
@@ -40,6 +39,13 @@ def test_ring_kat(kats):
     for r in kats["ring"]:
         got = O.ring_combine([np.array(p, dtype=np.uint32) for p in r["partials"]])
         assert (got == np.array(r["expect"], dtype=np.uint32)).all(), r["name"]
+
+
+def test_result_line_kat(kats):
+    for r in kats["lines"]:
+        got = O.result_lines(np.array(r["scores"], dtype=np.uint32))
+        assert got.tolist() == r["expect_lines"], r["name"]
+        assert L.result_lines(np.array(r["scores"], dtype=np.uint32).view(np.float32)).view(np.uint32).tolist() == r["expect_lines"]
 
 
 def test_labels_rule():

@@ -80,3 +80,18 @@ def test_cfg1_shape_and_threads():
 def _golden(name):
     import os
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+
+
+def test_blocked_loop_is_bit_identical_and_thread_count_is_bounded():
+    """The tree-blocked loop (the one timed as the CPU baseline) performs the same adds in the same per-tuple order."""
+    rng = np.random.default_rng(7)
+    for (D, T, F, K, S, n) in [(4, 16, 32, 2, 1, 1000), (6, 37, 64, 4, 2, 333), (9, 100, 128, 8, 2, 130), (3, 5, 8, 1, 1, 65),
+                               (12, 24, 256, 8, 1, 200), (5, 64, 16, 2, 2, 64)]:     # S*K*8 < T: trailing trees never walked
+        W, FI = L.synth_ensemble(T, D, F, seed=int(rng.integers(1 << 30)), bias=0.0)
+        x = L.synth_tuples(0, n, F, seed=int(rng.integers(1 << 30)), missing_ppm=30000)
+        wl, fl = L.pack_streams(W, FI, D)
+        cfg = oracle_cfg(D, K, S, L.MISSING_DEFAULT, F, T)
+        want = O.scores(cfg, wl, fl, x)
+        for th in (1, 3):
+            assert (O.scores_blocked(cfg, wl, fl, x, threads=th) == want).all(), (D, T, th)
+    assert 1 <= O.max_threads() <= O.online_cpus()
