@@ -80,6 +80,8 @@ struct dte_engine {
 
     // ---- partition of the current run (decided at `start` / load) ----
     uint32_t ndev_ring = 1;           // numDevs (reg 203[39:32])
+    int prog_partition = -1;          // how the RESIDENT ensemble was placed: 0 one device, 1 replicated, 2 chunks in ring order
+    int prog_pos2dev[kMaxRing];       // ... and on which devices (a run must use the same placement)
     bool group = false;               // ensemble-sharded lock-step group: data broadcast, partial scores ring-combined
     bool deal = false;                // data lines dealt round-robin in batches of deal_lines
     uint64_t deal_lines = 0;
@@ -160,6 +162,14 @@ int decode_geom(dte_engine* e, Geom& g) {
 // A run may reuse the resident ensemble only with the geometry it was loaded with (F and D fix the device
 // layout and the validated feature-index range; K, S and the missing pattern are free to change).
 int check_resident(dte_engine* e, const Geom& g) {
+    if (e->multi() && e->prog_partition >= 0) {
+        const int now = e->group ? 2 : 1;
+        if (now != e->prog_partition)
+            return fail(e, DTE_ERR_CONFIG, "reg 201 selects the %s partition but the resident ensemble was programmed %s",
+                        now == 2 ? "ensemble-sharded" : "data-sharded", e->prog_partition == 2 ? "in per-device chunks" : "replicated");
+        if (now == 2 && memcmp(e->pos2dev, e->prog_pos2dev, sizeof(int) * e->devs.size()))
+            return fail(e, DTE_ERR_CONFIG, "devices_list (registers 208-210) changed since the tree chunks were programmed: the ring order of the partial sums would change");
+    }
     for (Dev& d : e->devs) {
         if (!d.d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
         if (d.g.tuple_cls != g.tuple_cls || d.g.D != g.D)
@@ -659,14 +669,14 @@ int prepare_data_phase(dte_engine* e, bool need_ring) {
 int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_scores, uint8_t* h_labels) {
     Geom g;
     TRY(decode_geom(e, g));
-    TRY(check_resident(e, g));
-    if (n == 0) return DTE_OK;
     if (e->state == dte_engine::ST_TREES) return fail(e, DTE_ERR_STATE, "infer_host while the tree stream is being received");
     if (fragment_pending(e)) return fail(e, DTE_ERR_STATE, "a partial tuple is pending in the line stream");
     TRY(drain_all(e));
     const bool saved_group = e->group, saved_deal = e->deal;
-    e->g = g;
     if (e->multi()) TRY(decide_partition(e, g));
+    TRY(check_resident(e, g));
+    if (n == 0) return DTE_OK;
+    e->g = g;
     TRY(prepare_data_phase(e, false));
     const size_t tb = g.tuple_bytes();
     std::vector<uint64_t> enq0(e->devs.size());
@@ -790,6 +800,8 @@ int program_devices(dte_engine* e, const Geom& g) {
         TRY(pack_or_fail(e, g, e->tree_w[src].data(), lw, e->tree_f[src].data(), lf, 0, 0, pk));
         TRY(upload_ensemble(e, e->devs[0], pk));
     }
+    e->prog_partition = !e->multi() ? 0 : (replicate ? 1 : 2);
+    memcpy(e->prog_pos2dev, e->pos2dev, sizeof e->prog_pos2dev);
     return DTE_OK;
 }
 
@@ -1019,8 +1031,15 @@ int dte_stream_write(dte_t* e, const void* cl128, size_t n_lines) {
             // numcls_local_weights lines and the index stream every numcls_local_findexes lines, chunk i going to
             // devices_list[i % numDevs]; entry 0 is the host node itself (:160-178).  currDevID keeps rotating
             // from the weights into the index stream, as in the RTL.
-            const Flags f = decode_flags(e);
+            Flags f = decode_flags(e);
             const bool cut = f.multiple && !f.bcast_trees && f.ndev > 1;
+            if (cut && (e->regs[3] & 0xFFFFFFFFull) == 0 && wtotal % e->g.w_cls == 0) {
+                // extension: both 16-bit chunk fields left at 0 = "cut the trees evenly over numDevs" — chunks of more
+                // than 65535 lines (e.g. 1024 trees of depth 10 per device) cannot be written into reg 203
+                const uint64_t per = (wtotal / e->g.w_cls + f.ndev - 1) / f.ndev;
+                f.chunk_w = per * e->g.w_cls;
+                f.chunk_f = per * e->g.f_cls;
+            }
             if (cut && (f.chunk_f == 0 || (!e->multi() && e->node_index >= f.ndev)))
                 return fail(e, DTE_ERR_CONFIG, "reg 203: numcls_local_findexes=%llu numDevs=%u node=%u",
                             (unsigned long long)f.chunk_f, f.ndev, e->node_index);
@@ -1223,6 +1242,8 @@ int dte_load_ensemble(dte_t* e, const void* weight_cls, size_t n_weight_cls, con
         }
     }
     e->g = g;
+    e->prog_partition = !e->multi() ? 0 : (e->group ? 2 : 1);
+    memcpy(e->prog_pos2dev, e->pos2dev, sizeof e->prog_pos2dev);
     e->prog_seen = true; e->prog_open = false;
     e->t_prog0 = t0; e->t_prog1 = Clock::now();
     return DTE_OK;

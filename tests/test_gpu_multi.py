@@ -107,20 +107,27 @@ def test_ensemble_sharded_line_stream_ring_exact(devs):
         info = e.info()
         assert info["partition"] == 2 and info["num_trees"] == T
         assert out.size == (n // 4) * 4 and (out == want[: out.size]).all()
-        # a permuted devices_list (registers 208-210): ring position i served by device ID list[i]; same answer
-        perm = list(np.random.default_rng(G).permutation(G))
+        # host fast path on the same handle: scores AND labels, all n tuples (no line flush rule here)
+        sc, lb = e.infer_host(x)
+        assert (sc.view(np.uint32) == want).all() and (lb == O.labels(want)).all()
+        # a permuted devices_list (registers 208-210): ring position i served by device ID list[i]; same answer,
+        # and the resident chunks may not be reused under another ring order
+        perm = [int(v) for v in np.random.default_rng(G).permutation(G)]
+        if perm == list(range(G)):
+            perm = perm[1:] + perm[:1]
         r208 = 0
         for i, d in enumerate(perm):
-            r208 |= int(d) << (8 * i)
+            r208 |= d << (8 * i)
         e.softreg_write(208, r208)
+        with pytest.raises(E.DteError) as ei:
+            e.infer_host(x)
+        assert ei.value.code == -3
         e.start()
         e.stream_write(stream)
         out2 = e.stream_read(1 << 20).reshape(-1).view(np.uint32)
         assert (out2 == want[: out2.size]).all()
-        e.softreg_write(208, 0)
-        # host fast path on the same handle: scores AND labels, all n tuples (no line flush rule here)
-        sc, lb = e.infer_host(x)
-        assert (sc.view(np.uint32) == want).all() and (lb == O.labels(want)).all()
+        sc, _ = e.infer_host(x)
+        assert (sc.view(np.uint32) == want).all()
 
 
 @pytest.mark.parametrize("devs", DEVICE_LISTS, ids=lambda d: "gpus" + "".join(map(str, d)))
@@ -259,3 +266,28 @@ def test_default_stream_handle_orders_with_torch_work():
             got = ds.cpu().numpy().view(np.uint32)                                     # consumer on the default stream
             assert (got == want).all()
             del big
+
+
+@pytest.mark.parametrize("devs", DEVICE_LISTS, ids=lambda d: "gpus" + "".join(map(str, d)))
+def test_cpp_host_drives_the_whole_ring(devs):
+    """tools/dte_host.cpp over dte_create_multi: the C++ host (profiler-style parameters) runs both partitions on every GPU
+    of the list through registers + ONE line stream, and through the host fast path; checksums against the oracle."""
+    import json
+    import subprocess
+    from ddt_b200 import build as B
+    exe = B.build_host()
+    G = len(devs)
+    T, D, F, K, n = 16 * G, 6, 64, 4, 6000
+    W, FI = L.synth_ensemble(T, D, F)
+    x = L.synth_tuples(0, n, F)
+    wl, fl = L.pack_streams(W, FI, D)
+    full = O.scores(oracle_cfg(D, K, -(-T // (8 * K)), L.MISSING_DEFAULT, F, T), wl, fl, x, threads=8)
+    ring, _ = _ensemble_reference(W, FI, x, D, K, G)
+    for part, want in (("data", full), ("ensemble", ring)):
+        for mode in ("stream", "host"):
+            out = subprocess.run([exe, str(T), str(D), str(4 * F), str(n), str(K), mode, ",".join(map(str, devs)), part],
+                                 capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0, out.stderr
+            r = json.loads(out.stdout.strip().splitlines()[-1])
+            assert r["gpus"] == G and r["partition"] == part
+            assert r["results"] == n and r["score_words_sum"] == int(want.astype(np.uint64).sum()), (part, mode, r)

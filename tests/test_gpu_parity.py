@@ -484,6 +484,8 @@ def test_shipped_plan_headline_geometry_multi_tile(capsys):
     DTE_TUNE = pair=4 | ilp=8 | stages=2."""
     T, D, F, K, S = 24, 12, 256, 8, 1
     n = 160 * 148 * 2 + 77
+    if os.environ.get("DTE_TEST_SANITIZER"):          # instrumented runs: 16 trees, CTAs 0..2 still process two tiles each
+        T, n = 16, 160 * 148 + 333
     W, FI = L.synth_ensemble(T, D, F, seed=1201)
     x = L.synth_tuples(0, n, F, seed=1202, missing_ppm=15000)
     wl, fl = L.pack_streams(W, FI, D)

@@ -8,7 +8,11 @@
 // (weights | feature indexes | tuples), result lines back.  Prints tuples/s and a checksum the
 // tests compare with the Python path.
 //
-//   dte_host <N_trees> <Depth_tree> <Size_tuple_Bytes> <N_tuples> [clusters=8] [mode=stream|host]
+//   dte_host <N_trees> <Depth_tree> <Size_tuple_Bytes> <N_tuples> [clusters=8] [mode=stream|host] [gpus=0] [partition=data|ensemble]
+// gpus = comma list of CUDA ordinals, e.g. 0,1,2,3,4,5,6,7: ONE handle (dte_create_multi) then drives the whole ring:
+//   data     = BASELINE configs[4]: ensemble replicated (broadcast_trees), tuple lines dealt in batches over the GPUs
+//   ensemble = BASELINE configs[3]: N_trees cut into contiguous chunks (one per GPU), every tuple on every GPU,
+//              partial scores combined in ring order (aggreg_enabled)
 #include "../include/dte.h"
 
 #include <chrono>
@@ -42,6 +46,13 @@ int main(int argc, char** argv) {
     const uint64_t N_tuples = strtoull(argv[4], nullptr, 10);
     const uint32_t clusters = argc > 5 ? (uint32_t)atoi(argv[5]) : 8;
     const bool stream_mode = !(argc > 6 && !strcmp(argv[6], "host"));
+    std::vector<int> gpus;
+    if (argc > 7) {
+        for (const char* q = argv[7]; *q;) { gpus.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+    }
+    if (gpus.empty()) gpus.push_back(0);
+    const bool ensemble_part = argc > 8 && !strcmp(argv[8], "ensemble");
+    const uint32_t G = (uint32_t)gpus.size();
     const uint32_t missing = 0xBF800000u, F = Size_tuple_Bytes / 4, D = Depth_tree;
     const uint64_t seed_e = 0xD7EE5, seed_t = 0x7091E5;
 
@@ -51,7 +62,20 @@ int main(int argc, char** argv) {
         fprintf(stderr, "parameters outside the engine's CSR field ranges\n");
         return 2;
     }
-    if (dte_create(&e, 0)) { fprintf(stderr, "dte_create failed (no CUDA device; there is no CPU fallback)\n"); return 3; }
+    if (dte_create_multi(&e, gpus.data(), (int)G)) { fprintf(stderr, "dte_create_multi failed (no CUDA device; there is no CPU fallback)\n"); return 3; }
+    if (G > 1) {
+        // the multi-device flags a Catapult host writes (EngineCSR.sv:194-216): host_node | multiple_nodes | pcie_receiver_enabled
+        // + broadcast_trees (data dealt in batches of 1024 tuples)  or  broadcast_data | aggreg_enabled (tree chunks)
+        const uint64_t t_cls = Size_tuple_Bytes / 16;
+        uint64_t flags = 0x2 | 0x20 | 0x40;
+        flags |= ensemble_part ? (0x4 | 0x10) : 0x8;
+        regs[0] = flags | ((1024 * t_cls) << 32);
+        regs[2] = (uint64_t)G << 32;                     // numDevs; chunk fields 0 = cut the trees evenly
+        if (ensemble_part) {                             // S sized for one device's chunk
+            const uint64_t per = (N_trees + G - 1) / G, S = (per + 8 * clusters - 1) / (8 * clusters);
+            regs[4] = (regs[4] & ~(0xFFull << 36)) | (S << 36);
+        }
+    }
     for (int i = 0; i < 8; ++i) CHECK(dte_softreg_write(e, 201 + i, regs[i]));
 
     // ---- synthetic ensemble in the reference's stream layout (same law as layout.synth_ensemble) ----
@@ -104,8 +128,10 @@ int main(int argc, char** argv) {
     uint64_t exec_ns = 0;
     dte_softreg_read(e, 223, &exec_ns);
     printf("{\"N_trees\": %u, \"Depth_tree\": %u, \"Size_tuple_Bytes\": %u, \"N_tuples\": %llu, \"mode\": \"%s\", "
+           "\"gpus\": %u, \"partition\": \"%s\", "
            "\"tuples_per_s\": %.1f, \"exec_ns\": %llu, \"score_words_sum\": %llu, \"results\": %llu}\n",
-           N_trees, D, Size_tuple_Bytes, (unsigned long long)N_tuples, stream_mode ? "stream" : "host", N_tuples / dt,
+           N_trees, D, Size_tuple_Bytes, (unsigned long long)N_tuples, stream_mode ? "stream" : "host", G,
+           G == 1 ? "single" : (ensemble_part ? "ensemble" : "data"), N_tuples / dt,
            (unsigned long long)exec_ns, (unsigned long long)sum, (unsigned long long)n_out);
     dte_destroy(e);
     return 0;

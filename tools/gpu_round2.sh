@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 for stage in "$@"; do
 case "$stage" in
   tests)    timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -8 ;;
+  newtests) timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_parity.py -m gpu -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -25 ;;
   sanitize) bash tools/gpu_sanitize.sh 2>&1 | tee gpurun_out/sanitize_summary.txt ;;
   bench)    timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/bench_full.json ;;
   benchq)   timeout 600 python bench.py --tuples 8000000 --steps 5 --warmup 3 --no-cpu --e2e-tuples 1000000 > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; echo "benchq rc=$?"; cut -c1-300 gpurun_out/bench_q.json ;;
