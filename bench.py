@@ -441,8 +441,8 @@ def main():
         pg_lines = np.array(hx_lines, copy=True)                                # pageable copy of the same lines
         res = {}
         for label, buf in (("pinned", hx_lines), ("pageable", pg_lines)):
-            stream_run(buf, 1 << 22)
-            dt_s, got = stream_run(buf, 1 << 22)
+            stream_run(buf, 1 << 24)
+            dt_s, got = stream_run(buf, 1 << 24)
             ok = got == n_s // 4 and bool((out_lines.reshape(-1).view(np.uint32) == d_s[:n_s].cpu().numpy().view(np.uint32)).all())
             res[label] = {"tuples_per_s": n_s / dt_s, "bit_equal_to_device_path": ok}
         # the fast path on the same inputs, for the ratio
@@ -452,7 +452,7 @@ def main():
             es.infer_host(buf, out_scores=h_s[:n_s] if label == "pinned" else None, want_labels=False)
             t0 = time.perf_counter(); es.infer_host(buf, out_scores=h_s[:n_s] if label == "pinned" else None, want_labels=False)
             ref[label] = n_s / (time.perf_counter() - t0)
-        e2e_stream = {"api": "dte_softreg_write(201..208), start, dte_stream_write (trees, then tuple lines in 64 MiB writes), dte_stream_read_packets",
+        e2e_stream = {"api": "dte_softreg_write(201..208), start, dte_stream_write (trees, then tuple lines in 256 MiB writes), dte_stream_read_packets",
                       "tuples_per_step": int(n_s), "value": res["pinned"]["tuples_per_s"], "unit": "tuples/s",
                       "pinned_input": res["pinned"], "pageable_input": res["pageable"],
                       "infer_host_same_input": ref,
@@ -466,7 +466,7 @@ def main():
     extras = None
     if rank == 0 and not args.no_extras:
         extras = {}
-        for tag, (Tx, Dx, Fx, nx) in (("cfg2", (512, 8, 128, 10_000_000)), ("cfg4_shard", (1024, 10, 256, min(n, 20_000_000)))):
+        for tag, (Tx, Dx, Fx, nx) in (("cfg2", (512, 8, 128, min(10_000_000, n * F // 128))), ("cfg4_shard", (1024, 10, 256, min(n, 20_000_000)))):
             ex = ddt.Engine(local)
             ex.configure(Tx, Dx, 4 * Fx, clusters=K, missing_value=L.MISSING_DEFAULT)
             wx, fx = build_ensemble(Tx, Dx, Fx, seed=0xE5E if tag == "cfg4_shard" else None)

@@ -444,6 +444,16 @@ int land_dev(dte_engine* e, Dev& d, const unsigned char* src, size_t bytes) {
 Dev& host_dev(dte_engine* e) { return e->devs[(size_t)e->pos2dev[0]]; }
 const Dev& host_dev(const dte_engine* e) { return e->devs[(size_t)e->pos2dev[0]]; }
 
+// one launch of the ring-order combine; vector path only when every pointer is line-aligned
+cudaError_t launch_ring_combine(const RingParts& parts, int G, float* out, uint8_t* labels, size_t n, int sm_count, cudaStream_t st) {
+    bool vec = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (!labels || (reinterpret_cast<uintptr_t>(labels) & 3u) == 0);
+    for (int g = 0; g < G; ++g) vec = vec && (reinterpret_cast<uintptr_t>(parts.p[g]) & 15u) == 0;
+    const size_t work = vec ? n / 4 + 3 : n;
+    const unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, (size_t)sm_count * 8);
+    ring_combine_kernel<<<std::max(1u, blocks), 256, 0, st>>>(parts, G, out, labels, n, vec ? 1 : 0);
+    return cudaGetLastError();
+}
+
 int nccl_setup(dte_engine* e) {
     if (!e->nccl_comms.empty()) return DTE_OK;
     if (!e->nccl.load()) return fail(e, DTE_ERR_UNSUPPORTED, "DTE_OPT_COMBINE=1 needs libnccl.so.2 (dlopen failed)");
@@ -489,9 +499,7 @@ int submit_group(dte_engine* e, int b) {
         for (Dev& d : e->devs) CUDA_TRY(e, cudaStreamWaitEvent(h.s_main, d.slot[b].ev_walk, 0));
         RingParts parts;
         for (size_t r = 0; r < G; ++r) parts.p[r] = e->devs[(size_t)e->pos2dev[r]].slot[b].d_part + walked;   // ring order, host first
-        const unsigned blocks = (unsigned)std::min<size_t>((cnt / 4 + 255) / 256 + 1, (size_t)h.sm_count * 8);
-        ring_combine_kernel<<<blocks, 256, 0, h.s_main>>>(parts, (int)G, hs.d_sc + walked, labels ? hs.d_lb + walked : nullptr, cnt);
-        CUDA_TRY(e, cudaGetLastError());
+        CUDA_TRY(e, launch_ring_combine(parts, (int)G, hs.d_sc + walked, labels ? hs.d_lb + walked : nullptr, cnt, h.sm_count, h.s_main));
         h.kernel_launches++;
     } else {
         TRY(nccl_setup(e));
@@ -677,6 +685,8 @@ int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_
     TRY(check_resident(e, g));
     if (n == 0) return DTE_OK;
     e->g = g;
+    for (Dev& d : e->devs)                           // every chunk of this call starts on a fresh landing buffer
+        if (d.cap_tuples && d.slot[d.cur].fill) advance_slot(d);
     TRY(prepare_data_phase(e, false));
     const size_t tb = g.tuple_bytes();
     std::vector<uint64_t> enq0(e->devs.size());
@@ -1350,18 +1360,14 @@ int dte_ring_combine_device(dte_t* e, const float* const* d_parts, int n_parts, 
     if (!e || !d_parts || n_parts < 1 || n_parts > kMaxRing || (n && !d_out)) return DTE_ERR_ARG;
     RingParts parts;
     for (int g = 0; g < n_parts; ++g) {
-        if (!d_parts[g] || (reinterpret_cast<uintptr_t>(d_parts[g]) & 15u)) return fail(e, DTE_ERR_ARG, "part %d: null or not 16-byte aligned", g);
+        if (!d_parts[g] || (reinterpret_cast<uintptr_t>(d_parts[g]) & 3u)) return fail(e, DTE_ERR_ARG, "part %d: null or not 4-byte aligned", g);
         parts.p[g] = d_parts[g];
     }
-    if ((reinterpret_cast<uintptr_t>(d_out) & 15u) || (d_labels && (reinterpret_cast<uintptr_t>(d_labels) & 3u)))
-        return fail(e, DTE_ERR_ARG, "output buffers must be 16-byte (scores) / 4-byte (labels) aligned");
     if (!n) return DTE_OK;
     Dev& d = e->devs[0];
     CUDA_TRY(e, cudaSetDevice(d.ordinal));
     cudaStream_t st = pick_stream(d, cuda_stream);
-    const unsigned blocks = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)d.sm_count * 8);
-    ring_combine_kernel<<<blocks, 256, 0, st>>>(parts, n_parts, d_out, d_labels, n);
-    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, launch_ring_combine(parts, n_parts, d_out, d_labels, n, d.sm_count, st));
     d.kernel_launches++;
     if (!cuda_stream) CUDA_TRY(e, cudaStreamSynchronize(st));
     return DTE_OK;

@@ -638,11 +638,18 @@ __device__ __forceinline__ uint4 ldg128_peer(const void* p) {   // read-once pee
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ float ld_peer32(const float* p) {
+    float v;
+    asm volatile("ld.global.relaxed.sys.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 __global__ void __launch_bounds__(256) ring_combine_kernel(const RingParts parts, int G, float* __restrict__ out,
-                                                           uint8_t* __restrict__ labels, unsigned long long n) {
+                                                           uint8_t* __restrict__ labels, unsigned long long n, int vec) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long nline = n >> 2;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nline; i += stride) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // vec = 1: every pointer is 16-byte aligned (labels 4-byte): whole result lines per thread
+    const unsigned long long nline = vec ? n >> 2 : 0;
+    for (unsigned long long i = tid; i < nline; i += stride) {
         uint4 a = ldg128_peer(reinterpret_cast<const uint4*>(parts.p[0]) + i);
         float s0 = __uint_as_float(a.x), s1 = __uint_as_float(a.y), s2 = __uint_as_float(a.z), s3 = __uint_as_float(a.w);
 #pragma unroll 4
@@ -657,14 +664,13 @@ __global__ void __launch_bounds__(256) ring_combine_kernel(const RingParts parts
             reinterpret_cast<uint32_t*>(labels)[i] = l;
         }
     }
-    // tuples past the last whole line (n % 4): scalar tail, first thread of the grid
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (unsigned long long i = nline << 2; i < n; ++i) {
-            float s = parts.p[0][i];
-            for (int g = 1; g < G; ++g) s = fadd_ref(parts.p[g][i], s);
-            out[i] = s;
-            if (labels) labels[i] = s > 0.0f ? 1 : 0;
-        }
+    // the rest one tuple at a time: the n % 4 tail, or everything when a pointer is not line-aligned (a partial
+    // flush of the landing buffer can start at any tuple)
+    for (unsigned long long i = (nline << 2) + tid; i < n; i += stride) {
+        float s = ld_peer32(parts.p[0] + i);
+        for (int g = 1; g < G; ++g) s = fadd_ref(ld_peer32(parts.p[g] + i), s);
+        out[i] = s;
+        if (labels) labels[i] = s > 0.0f ? 1 : 0;
     }
 }
 __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long seed, unsigned long long idx) {

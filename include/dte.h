@@ -159,7 +159,7 @@ int dte_ring_add_device(dte_t* engine, const float* d_a, const float* d_b, float
  * add = add.rn.ftz.f32 — bit-exact with the reference's aggregate mode (ResultsCombiner.sv:292-311,359-368), and
  * labels[i] = out[i] > 0 (NULL to skip).  The part pointers may be buffers of PEER GPUs (dte_ipc_open, or peer access
  * inside one process): the kernel reads them over NVLink, so the cross-device combine costs one launch and no
- * collective.  n_parts <= 20 (devices_list); pointers 16-byte aligned. */
+ * collective.  n_parts <= 20 (devices_list); 16-byte aligned pointers take the vector path (one result line per thread). */
 int dte_ring_combine_device(dte_t* engine, const float* const* d_parts, int n_parts, size_t n, float* d_out,
                             uint8_t* d_labels, void* cuda_stream);
 
