@@ -85,3 +85,24 @@ def build_model(force=False):
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
     return MODEL_OUT
+
+
+PACK_SRC = os.path.join(HERE, "..", "tools", "pack_check.cu")
+PACK_OUT = os.path.join(HERE, "..", "tools", "pack_check")
+
+
+def build_pack_check(force=False):
+    """Host-only checker of the ensemble repacker (tools/pack_check.cu); used by the CPU test tier."""
+    deps = [PACK_SRC] + DEPS[1:3]
+    if not force and os.path.exists(PACK_OUT) and all(os.path.getmtime(PACK_OUT) >= os.path.getmtime(d) for d in deps):
+        return PACK_OUT
+    nvcc = nvcc_path()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found")
+    cmd = [nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", PACK_OUT, PACK_SRC]
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return PACK_OUT

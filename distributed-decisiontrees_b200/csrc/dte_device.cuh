@@ -115,18 +115,28 @@ inline int pack_ensemble(const Geom& g, const unsigned char* wl, size_t n_wl, co
     const uint32_t* Wall = reinterpret_cast<const uint32_t*>(wl);
     const uint16_t* Fall = reinterpret_cast<const uint16_t*>(fl);
 
-    // pass 1: contract check + widest feature index
+    // pass 1: contract check + widest feature index.  Early leaves: bit 14 of a node's index word says "my children are
+    // leaves" (DTPU.sv:596,661,712) — the walk then ends at the child cell W[2n+1+right], whatever D says.  (The RTL
+    // freezes node_offset WITHOUT the direction bit while its memory address keeps advancing, so with >= 1 level left
+    // it reads a wrong cell; the build-defined rule here is the evident intent, SURVEY R3 / DESIGN.md.)  Nodes below
+    // an early leaf are unreachable: their words are don't-care and are not validated.
+    const uint32_t n_int = (1u << D) - 1;
     uint32_t max_f = 0;
+    bool any_early = false;
+    std::vector<uint8_t> dead(n_int);
     for (uint32_t t = 0; t < count; ++t) {
         const uint16_t* fi = Fall + (size_t)(first + t) * fstride;
-        for (uint32_t i = 0; i + 1 < (1u << D); ++i) {
+        std::fill(dead.begin(), dead.end(), 0);
+        for (uint32_t i = 0; i < n_int; ++i) {
+            const bool early = !dead[i] && (fi[i] & 0x4000u);
+            if (dead[i] || early) {
+                if (2 * i + 2 < n_int) dead[2 * i + 1] = dead[2 * i + 2] = 1;
+                any_early |= early && (2 * i + 2 < n_int);
+                if (dead[i]) continue;
+            }
             const uint32_t f = fi[i] & 0x7FFu;
             if (f >= F) {
                 snprintf(buf, sizeof buf, "tree %u node %u: feature index %u >= %u features", first + t, i, f, F);
-                msg = buf; return -4;
-            }
-            if (fi[i] & 0x4000u) {
-                snprintf(buf, sizeof buf, "tree %u node %u: bit 14 (next-node-is-leaf) set; complete trees only", first + t, i);
                 msg = buf; return -4;
             }
             max_f = std::max(max_f, f);
@@ -153,6 +163,24 @@ inline int pack_ensemble(const Geom& g, const unsigned char* wl, size_t n_wl, co
         } else {
             std::copy(W, W + ((2u << D) - 1), Wk.begin());
             std::copy(FI, FI + ((1u << D) - 1), Fk.begin());
+            if (any_early) {
+                // expand early leaves into complete subtrees whose every leaf is the early leaf's value: the same
+                // function of x on a complete tree, so the kernels need no early-exit path
+                std::vector<uint8_t>& konst = dead;
+                std::fill(konst.begin(), konst.end(), 0);
+                for (uint32_t i = 0; i < n_int; ++i) {
+                    const uint32_t l = 2 * i + 1, r = 2 * i + 2;
+                    if (konst[i]) {                       // inside a constant subtree: value travels in Wk[i]
+                        const uint32_t v = Wk[i];
+                        Wk[l] = v; Wk[r] = v;
+                        if (r < n_int) konst[l] = konst[r] = 1;
+                        Wk[i] = 0; Fk[i] = 0;             // any threshold / feature 0: both ways lead to v
+                    } else if ((Fk[i] & 0x4000u) && r < n_int) {
+                        konst[l] = konst[r] = 1;          // children are leaves: W[l], W[r] already hold their values
+                    }
+                    Fk[i] &= (uint16_t)~0x4000u;
+                }
+            }
         }
         uint2* tp = out.top.data() + (size_t)t * top_stride;
         for (uint32_t n = 0; n + 1 < (1u << Dtop); ++n) {

@@ -128,8 +128,27 @@ uint32_t dteo_leaf(const dteo_cfg* c, const uint32_t* w, const uint16_t* fi, con
         int smaller = ((int32_t)v < (int32_t)thr);
         int right = missing ? ((f >> 13) & 1) : !smaller;
         n = 2 * n + 1 + (uint32_t)right;
+        /* bit 14 "next node is leaf" (DTPU.sv:596,661,712): the children of this node are leaves, the walk ends in
+           the child's cell.  BUILD-DEFINED where the RTL is broken: the RTL freezes node_offset without the
+           direction bit while its read address keeps advancing, so with levels left it returns a wrong cell; the
+           address-literal walker below keeps that behaviour, this one implements the evident intent. */
+        if (f & 0x4000u) break;
     }
     return w[n];
+}
+
+/* reachable internal nodes must index inside the tuple; nodes below an early leaf are don't-care */
+static int check_tree(const dteo_cfg* c, const uint16_t* fi, size_t F) {
+    const uint32_t n_int = (1u << c->num_levels) - 1;
+    uint8_t* dead = (uint8_t*)calloc(n_int ? n_int : 1, 1);
+    if (!dead) return -5;
+    int rc = 0;
+    for (uint32_t i = 0; i < n_int && !rc; ++i) {
+        if ((dead[i] || (fi[i] & 0x4000u)) && 2 * i + 2 < n_int) dead[2 * i + 1] = dead[2 * i + 2] = 1;
+        if (!dead[i] && (fi[i] & 0x7FFu) >= F) rc = -3;
+    }
+    free(dead);
+    return rc;
 }
 
 /* 8-leaf reduce tree ((l0+l1)+(l2+l3))+((l4+l5)+(l6+l7)): FPAddersReduceTree.sv:90-125, output
@@ -242,13 +261,10 @@ int dteo_scores(const dteo_cfg* c, const void* weights_cls, const void* findex_c
     const uint16_t* FI = (const uint16_t*)findex_cls;
     const uint32_t* X = (const uint32_t*)tuple_cls;
     const size_t F = (size_t)c->tuple_cls * 4;
-    /* out-of-contract inputs are refused, not guessed: feature index beyond the tuple, bit 14 set */
+    /* out-of-contract inputs are refused, not guessed: a reachable feature index beyond the tuple */
     for (uint32_t t = 0; t < c->num_trees; ++t) {
-        const uint16_t* fi = FI + (size_t)t * c->tree_f_cls * 8;
-        for (uint32_t i = 0; i + 1 < (1u << c->num_levels); ++i) {
-            if ((fi[i] & 0x7FFu) >= F) return -3;
-            if (fi[i] & 0x4000u) return -4;
-        }
+        int rc = check_tree(c, FI + (size_t)t * c->tree_f_cls * 8, F);
+        if (rc) return rc;
     }
     if (threads < 1) threads = 1;
     if ((size_t)threads > n) threads = n ? (int)n : 1;
@@ -329,11 +345,8 @@ int dteo_scores_blocked(const dteo_cfg* c, const void* weights_cls, const void* 
     const uint32_t* X = (const uint32_t*)tuple_cls;
     const size_t F = (size_t)c->tuple_cls * 4;
     for (uint32_t t = 0; t < c->num_trees; ++t) {
-        const uint16_t* fi = FI + (size_t)t * c->tree_f_cls * 8;
-        for (uint32_t i = 0; i + 1 < (1u << c->num_levels); ++i) {
-            if ((fi[i] & 0x7FFu) >= F) return -3;
-            if (fi[i] & 0x4000u) return -4;
-        }
+        int rc = check_tree(c, FI + (size_t)t * c->tree_f_cls * 8, F);
+        if (rc) return rc;
     }
     if (threads < 1) threads = 1;
     size_t nblocks = (n + DTEO_BLOCK - 1) / DTEO_BLOCK;

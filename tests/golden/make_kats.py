@@ -191,6 +191,23 @@ cases.append(dict(
     expect=[f(2147516416.0)],
 ))
 
+# 14 -- early leaves, bit 14 "next node is leaf" (DTPU.sv:596,661,712).  BUILD-DEFINED RULE (the RTL is broken here: it
+#       freezes node_offset WITHOUT the direction bit while the read address keeps advancing, so an early leaf with levels
+#       left reads a wrong cell): when a node carries bit 14 the walk ends in its child's cell W[2n+1+right].
+#       D=3: node 1 carries bit 14 -> cells W[3], W[4] are leaves (10, 20); node 2's side is a normal 3-level walk.
+#       Tree B: bit 14 on the ROOT -> a one-level tree, leaves W[1], W[2]; everything below is don't-care (index 99 > F).
+early_a = {"W": [f(0.5), f(0.5), f(0.5), f(10.0), f(20.0), f(0.5), f(0.5)] + [f(float(100 + i)) for i in range(8)],
+           "FI": [0, 1 | (1 << 14), 2, 99, 99, 3, 3]}
+early_b = {"W": [f(0.5), f(1000.0), f(2000.0)] + [0] * 12, "FI": [1 | (1 << 14)] + [99] * 6}
+cases.append(dict(
+    name="early_leaf_bit14", D=3, K=1, S=1, missing=MISS, F=4, rtl_literal=False,
+    why="t0 x=[L,R,-,-]: A 0-L->1 (bit14) x1=R -> cell W[4]=20; B root bit14 x1=R -> W[2]=2000: 2020.  t1 x=[L,L]: 10+1000=1010.  "
+        "t2 x=[R,L,R,R]: A 0-R->2 (x2=R)->6 (x3=R)-> leaf W[14]=107; B x1=L -> 1000: 1107",
+    trees=[early_a, early_b] + [const_tree(3, 0)] * 6,
+    tuples=[[lo, hi, 0, 0], [lo, lo, 0, 0], [hi, lo, hi, hi]],
+    expect=[f(2020.0), f(1010.0), f(1107.0)],
+))
+
 # result packing (ResultsCombiner.sv:132-162): 4 consecutive results per line, word j = tuple 4m+j; a trailing group
 # of fewer than 4 results is never emitted (:153-155, curr_word only wraps on the 4th fill)
 lines_kat = dict(

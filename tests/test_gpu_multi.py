@@ -214,7 +214,7 @@ def test_result_queue_back_pressure_and_restart_geometry_check():
         e.stream_write(lines[: 8 * tl])
         assert (e.stream_read(10).reshape(-1).view(np.uint32) == want[:8]).all()
         # a failed load leaves the resident ensemble and its geometry in place
-        bad = FI.copy(); bad[0, 0] = 31 | (1 << 14)
+        bad = FI.copy(); bad[0, 0] = 40                        # feature index >= F
         with pytest.raises(E.DteError):
             e.load_ensemble(*L.pack_streams(W, bad, D))
         sc, _ = e.infer_host(x[:16])

@@ -221,9 +221,9 @@ def test_error_paths():
         with pytest.raises(E.DteError) as ei:
             e.load_ensemble(*L.pack_streams(W, bad, 3))
         assert ei.value.code == -4
-        bad = FI.copy(); bad[0, 0] |= 1 << 14                  # early-leaf bit: out of contract
-        with pytest.raises(E.DteError):
-            e.load_ensemble(*L.pack_streams(W, bad, 3))
+        early = FI.copy(); early[0, 0] |= 1 << 14              # early-leaf bit on the root: a one-level tree, legal
+        early[0, 1:] = 200                                     # ... and everything below it is don't-care
+        e.load_ensemble(*L.pack_streams(W, early, 3))
         with pytest.raises(E.DteError):                       # truncated index stream
             e.load_ensemble(wl, fl[:-1])
         e.load_ensemble(wl, fl)
@@ -500,3 +500,24 @@ def test_shipped_plan_headline_geometry_multi_tile(capsys):
         got, lab = run_engine_host(e, x, E.DTE_KERNEL_AUTO)
         assert e.info()["tuples_per_cta"] * 148 < n
     assert (got == want).all() and (lab == O.labels(want)).all()
+
+
+def test_early_leaves_random_ensembles():
+    """Bit 14 ("next node is leaf", DTPU.sv:596,661,712) with the build-defined rule (walk ends in the child's cell):
+    random early leaves at random levels, garbage below them; every kernel variant equals the oracle."""
+    rng = np.random.default_rng(14)
+    for D, T, F in [(3, 8, 8), (6, 24, 32), (9, 16, 64), (12, 8, 256)]:
+        W, FI = L.synth_ensemble(T, D, F, seed=1400 + D)
+        n_int = (1 << D) - 1
+        for t in range(T):
+            for _ in range(int(rng.integers(0, 6))):
+                lvl = int(rng.integers(0, D))
+                i = (1 << lvl) - 1 + int(rng.integers(0, 1 << lvl))
+                FI[t, i] |= 1 << 14
+                # everything below node i's children is unreachable: fill with out-of-range indexes / noise
+                lo, hi = 2 * (2 * i + 1) + 1, 2 * (2 * i + 2) + 2
+                while lo < n_int:
+                    FI[t, lo:min(hi, n_int - 1) + 1] = 0x7FF
+                    lo, hi = 2 * lo + 1, 2 * hi + 2
+        x = L.synth_tuples(0, 777, F, seed=1500 + D, missing_ppm=20000)
+        check_case(W, FI, x, D, 2, -(-T // 16))

@@ -81,3 +81,42 @@ def test_performance_model_cli():
     m = re.search(r"walk-bound\s*:\s*([0-9.e+]+)", txt)
     assert m and float(m.group(1)) > 1e7
     assert subprocess.run([exe], capture_output=True).returncode == 2
+
+
+def test_repacker_on_the_cpu_against_the_oracle(tmp_path):
+    """The device layout (8-byte top records, 32/64-byte bottom records, D = 1 extension, early leaves expanded into
+    complete subtrees) decoded on the HOST exactly as the kernels decode it (tools/pack_check.cu) gives the oracle's
+    leaf for every (tuple, tree) — the repacker is covered without a GPU."""
+    import subprocess
+    import numpy as np
+    from ddt_b200 import build as B
+    from helpers import oracle_cfg
+    from oracle import oracle as O
+    exe = B.build_pack_check()
+    rng = np.random.default_rng(3)
+    for D, T, F, early in [(1, 5, 4, False), (2, 9, 8, False), (3, 8, 8, True), (5, 16, 32, True), (8, 7, 600, True), (12, 3, 256, True), (10, 4, 2044, False)]:
+        W, FI = L.synth_ensemble(T, D, F, seed=50 + D)
+        n_int = (1 << D) - 1
+        if early:
+            for t in range(T):
+                for _ in range(3):
+                    lvl = int(rng.integers(0, D))
+                    FI[t, (1 << lvl) - 1 + int(rng.integers(0, 1 << lvl))] |= 1 << 14
+        x = L.synth_tuples(0, 97, F, seed=60 + D, missing_ppm=30000)
+        wl, fl = L.pack_streams(W, FI, D)
+        for name, arr in (("w", wl), ("f", fl), ("x", x)):
+            np.ascontiguousarray(arr).tofile(tmp_path / (name + ".bin"))
+        out = subprocess.run([exe, str(D), str(F), str(T), "97", str(L.MISSING_DEFAULT), str(tmp_path / "w.bin"), str(tmp_path / "f.bin"),
+                              str(tmp_path / "x.bin")], capture_output=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        got = np.frombuffer(out.stdout, dtype=np.uint32).reshape(97, T)
+        cfg = oracle_cfg(D, 1, 1, L.MISSING_DEFAULT, F, T)
+        w_cls, f_cls = L.tree_cls(D)
+        lib = O.lib()
+        import ctypes as C
+        for t in range(T):
+            wt = np.ascontiguousarray(wl.reshape(T, -1)[t]); ft = np.ascontiguousarray(fl.reshape(T, -1)[t])
+            for i in range(0, 97, 7):
+                xi = np.ascontiguousarray(x[i])
+                want = lib.dteo_leaf(C.byref(cfg), wt.ctypes.data, ft.ctypes.data, xi.ctypes.data)
+                assert got[i, t] == want, (D, t, i)
