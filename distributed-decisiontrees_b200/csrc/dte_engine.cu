@@ -1331,6 +1331,19 @@ int dte_infer_host(dte_t* e, const void* h_tuples, size_t n, float* h_scores, ui
     return infer_host(e, static_cast<const unsigned char*>(h_tuples), n, h_scores, h_labels);
 }
 
+int dte_host_alloc(dte_t* e, size_t bytes, void** h_ptr) {
+    if (!e || !h_ptr || !bytes) return DTE_ERR_ARG;
+    CUDA_TRY(e, cudaSetDevice(e->devs[0].ordinal));
+    CUDA_TRY(e, cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable));
+    return DTE_OK;
+}
+
+int dte_host_free(dte_t* e, void* h_ptr) {
+    if (!e || !h_ptr) return DTE_ERR_ARG;
+    CUDA_TRY(e, cudaFreeHost(h_ptr));
+    return DTE_OK;
+}
+
 int dte_labels_device(dte_t* e, const float* d_scores, size_t n, uint8_t* d_labels, void* cuda_stream) {
     if (!e || (n && (!d_scores || !d_labels))) return DTE_ERR_ARG;
     if (!n) return DTE_OK;

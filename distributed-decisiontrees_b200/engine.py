@@ -40,6 +40,8 @@ ABI = [
     ("dte_ipc_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     ("dte_ipc_open", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     ("dte_ipc_close", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("dte_host_alloc", C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("dte_host_free", C.c_int, [C.c_void_p, C.c_void_p]),
     ("dte_labels_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     ("dte_ring_add_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("dte_csr_from_profile", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _u64p]),
@@ -285,6 +287,22 @@ class Engine:
 
     def ipc_close(self, ptr, owner):
         self._check(self._lib.dte_ipc_close(self._h, C.c_void_p(int(ptr)), 1 if owner else 0))
+
+    def host_alloc(self, shape, dtype):
+        """numpy array over page-locked, portable host memory (dte_host_alloc); release with host_free(array)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        self._check(self._lib.dte_host_alloc(self._h, n, C.byref(ptr)))
+        buf = (C.c_char * n).from_address(ptr.value)
+        a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._host_ptrs = getattr(self, "_host_ptrs", {})
+        self._host_ptrs[a.ctypes.data] = ptr.value
+        return a
+
+    def host_free(self, array):
+        ptr = getattr(self, "_host_ptrs", {}).pop(array.ctypes.data, None)
+        if ptr is not None:
+            self._check(self._lib.dte_host_free(self._h, C.c_void_p(ptr)))
 
     def labels_device(self, d_scores, n, d_labels, stream=None):
         self._check(self._lib.dte_labels_device(self._h, _ptr(d_scores), int(n), _ptr(d_labels),

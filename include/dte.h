@@ -148,6 +148,12 @@ int dte_ipc_close(dte_t* engine, void* d_ptr, int owner);
  * h_scores (and h_labels if not NULL) are complete.  Pinned host buffers give full PCIe speed. */
 int dte_infer_host(dte_t* engine, const void* h_tuples, size_t n, float* h_scores, uint8_t* h_labels);
 
+/* Page-locked host memory every device of the handle can DMA from / to at full PCIe speed (cudaHostAlloc, portable):
+ * what a Catapult host gets from the driver's DMA-buffer allocator (the slot buffers behind rtl/PCIeShim.sv:99-141).
+ * Pageable memory works everywhere too, through the CUDA driver's staging copies (about 5 x slower). */
+int dte_host_alloc(dte_t* engine, size_t bytes, void** h_ptr);
+int dte_host_free(dte_t* engine, void* h_ptr);
+
 /* labels[i] = scores[i] > 0.0f on the device (used after a cross-device reduce). */
 int dte_labels_device(dte_t* engine, const float* d_scores, size_t n, uint8_t* d_labels, void* cuda_stream);
 
