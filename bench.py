@@ -276,10 +276,12 @@ def main():
         return 1
     torch.cuda.set_device(local)
     dist = None
+    host_group = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")                 # host-only barrier: an NCCL barrier spins ON the GPUs
 
     def barrier():
         torch.cuda.synchronize()
@@ -511,6 +513,7 @@ def main():
                 multi = c_abi_multi(ddt, E, torch, world, F, K, wl, fl, T, D, h_x, n_e)
             except Exception as ex:                               # noqa: BLE001
                 multi = {"error": str(ex)}
+        dist.barrier(group=host_group)         # the idle ranks wait on the host, their GPUs stay free for rank 0's handle
         barrier()
 
     if rank == 0:
