@@ -26,15 +26,10 @@ enum { KERNEL_AUTO = 0, KERNEL_GENERIC = 1, KERNEL_TILE = 2, KERNEL_TILE_STAGED 
 //  chunk: tuples per landing slot)
 struct Tune {
     int ilp = 0, stages = 0, warps = 0, pair = 0, fill = 0, phased = -1;
-    int c16 = -1;             // compact (6-byte) tops in the staged ring: -1 default, 0 off, 1 on
     size_t chunk = 0;
 };
-#ifndef DTE_C16_DEFAULT
-#define DTE_C16_DEFAULT 0
-#endif
 
 inline void parse_tune(Tune& t) {
-    if (const char* c = getenv("DTE_C16")) t.c16 = atoi(c);      // compact tops on/off without touching DTE_TUNE
     const char* s = getenv("DTE_TUNE");
     if (!s) return;
     std::string str(s);
@@ -52,7 +47,6 @@ inline void parse_tune(Tune& t) {
             else if (k == "pair") t.pair = (int)v;
             else if (k == "fill") t.fill = (int)v;
             else if (k == "phased") t.phased = (int)v;
-            else if (k == "c16") t.c16 = (int)v;
             else if (k == "chunk") t.chunk = (size_t)v;
         }
         if (comma == std::string::npos) break;
@@ -71,7 +65,6 @@ struct Plan {               // how the next walk will be launched
     int variant = KERNEL_GENERIC;
     int ilp = 8, pair = 1, nstages = 0, nwarps = 0;   // nwarps = consumer warps = groups * pair
     bool wide = false;
-    bool c16 = false;                                  // staged ring holds compact 6-byte tops
     size_t smem = 0;
     int threads() const { return variant == KERNEL_GENERIC ? 128 : 32 * (nwarps + (variant == KERNEL_TILE_STAGED ? 1 : 0)); }
     int thread_bound() const {                         // NT of the instantiation that will run (see dt_walk_tile)
@@ -92,25 +85,11 @@ struct PackedEnsemble {
     bool wide = false;
     std::vector<uint2> top;
     std::vector<uint4> bottom;
-    // compact tops for the staged ring (dte_kernels.cuh "compact tops"): per tree [A32][Alo][B32][Blo]
-    std::vector<unsigned char> top16;
-    uint32_t c16_nA = 0;              // node slots in part A (== top_stride when the ring refill is not phased)
-    uint32_t c16_Lw = 0xFFFFFFFFu;    // last level of part A, 0xFFFFFFFF = one part
 };
-
-// Level after which a tree top is split for the phased ring refill (0xFFFFFFFF: no split).  Measured
-// (profiles/r01_summary.md): +7 % at D = 12 (64 KiB stage), -4 % at D <= 10 (<= 16 KiB stage, the refill is already
-// cheap there and the extra barrier hand-offs cost more than they hide).  DTE_TUNE phased=k moves the split k-1
-// levels further up (smaller part A).  The compact layout is built around this split, so it is fixed at load time.
-inline uint32_t phased_split(uint32_t Dtop, const Tune& tune) {
-    const bool phased = tune.phased >= 1 || (tune.phased == -1 && Dtop >= 10);
-    const uint32_t up = tune.phased > 1 ? (uint32_t)tune.phased - 1 : 0;
-    return (phased && Dtop >= 3 + up) ? Dtop - 3 - up : 0xFFFFFFFFu;
-}
 
 // returns 0 or a negative dte_status; *msg receives the reason
 inline int pack_ensemble(const Geom& g, const unsigned char* wl, size_t n_wl, const unsigned char* fl, size_t n_fl,
-                         uint32_t first, uint32_t count, PackedEnsemble& out, std::string& msg, const Tune& tune = Tune()) {
+                         uint32_t first, uint32_t count, PackedEnsemble& out, std::string& msg) {
     char buf[256];
     if (n_wl % g.w_cls) {
         snprintf(buf, sizeof buf, "weights stream: %zu lines is not a multiple of %u lines per tree", n_wl, g.w_cls);
@@ -172,11 +151,6 @@ inline int pack_ensemble(const Geom& g, const unsigned char* wl, size_t n_wl, co
     out.bottom.assign((size_t)Tpad * nb * BV, make_uint4(0, 0, 0, 0));
     std::vector<uint32_t> Wk((2u << Dk) - 1);
     std::vector<uint16_t> Fk((1u << Dk) - 1);
-    // compact tops (staged ring only: at least 3 staged levels)
-    const bool want16 = Dtop >= 3;
-    out.c16_Lw = want16 ? phased_split(Dtop, tune) : 0xFFFFFFFFu;
-    out.c16_nA = !want16 ? 0 : (out.c16_Lw == 0xFFFFFFFFu ? top_stride : (2u << out.c16_Lw));
-    out.top16.assign(want16 ? (size_t)Tpad * top_stride * 6 : 0, 0);
     for (uint32_t t = 0; t < count; ++t) {
         const uint32_t* W = Wall + (size_t)(first + t) * wstride;
         const uint16_t* FI = Fall + (size_t)(first + t) * fstride;
@@ -212,21 +186,6 @@ inline int pack_ensemble(const Geom& g, const unsigned char* wl, size_t n_wl, co
         for (uint32_t n = 0; n + 1 < (1u << Dtop); ++n) {
             const uint32_t f = Fk[n] & 0x7FFu, mr = (Fk[n] >> 13) & 1u;
             tp[n] = make_uint2(Wk[n], f | ((8u + 8u * mr) << 16));
-        }
-        if (want16) {
-            const uint32_t nA = out.c16_nA, nB = top_stride - nA;
-            unsigned char* blk = out.top16.data() + (size_t)t * top_stride * 6;
-            uint32_t* A32 = reinterpret_cast<uint32_t*>(blk);
-            uint16_t* Alo = reinterpret_cast<uint16_t*>(blk + 4 * (size_t)nA);
-            uint32_t* B32 = reinterpret_cast<uint32_t*>(blk + 6 * (size_t)nA);
-            uint16_t* Blo = reinterpret_cast<uint16_t*>(blk + 6 * (size_t)nA + 4 * (size_t)nB);
-            for (uint32_t n = 0; n + 1 < (1u << Dtop); ++n) {
-                const uint32_t f = Fk[n] & 0x7FFu, mr = (Fk[n] >> 13) & 1u;
-                const uint32_t w32 = (Wk[n] & 0xFFFF0000u) | (mr << 15) | f;
-                const uint16_t lo = (uint16_t)(Wk[n] & 0xFFFFu);
-                if (n + 1 < nA) { A32[n] = w32; Alo[n] = lo; }                 // levels 0..Lw (all of them when not split)
-                else { B32[n - (nA - 1)] = w32; Blo[n - (nA - 1)] = lo; }
-            }
         }
         uint4* bp = out.bottom.data() + (size_t)t * nb * BV;
         for (uint32_t j = 0; j < nb; ++j) {
@@ -280,8 +239,6 @@ struct Dev {
     bool wide = false;
     uint2* d_top = nullptr;
     uint4* d_bottom = nullptr;
-    unsigned char* d_top16 = nullptr; // compact tops for the staged ring (nullptr: not built)
-    uint32_t c16_nA = 0, c16_Lw = 0xFFFFFFFFu;
     uint64_t ensemble_bytes = 0;
 
     // ---- landing slots ----
@@ -306,8 +263,8 @@ struct Dev {
 };
 
 // ---- launch planning ---------------------------------------------------------------------------
-inline size_t tile_smem(uint32_t F, int groups, int trees_per_stage, int nstages, uint32_t top_stride, int node_bytes = 8) {
-    return (size_t)kHdrBytes + (size_t)nstages * trees_per_stage * top_stride * node_bytes + (size_t)F * 32 * groups * 4;
+inline size_t tile_smem(uint32_t F, int groups, int trees_per_stage, int nstages, uint32_t top_stride) {
+    return (size_t)kHdrBytes + (size_t)nstages * trees_per_stage * top_stride * 8 + (size_t)F * 32 * groups * 4;
 }
 
 inline Plan make_plan(const Dev& d, const Tune& tune, int want) {
@@ -315,11 +272,9 @@ inline Plan make_plan(const Dev& d, const Tune& tune, int want) {
     p.wide = d.wide;
     const uint32_t F = d.g.F();
     const size_t budget = (size_t)d.smem_optin;
-    const bool c16 = d.d_top16 && (tune.c16 == 1 || (tune.c16 == -1 && DTE_C16_DEFAULT));
-    const int nbytes = c16 ? 6 : 8;
     // tuple groups (32 tuples, F*128 B of shared memory each) that fit next to the ring
     auto max_groups = [&](int ilp, int pair, int nstages) -> int {
-        const size_t fixed = tile_smem(F, 0, ilp * pair, nstages, d.top_stride, nstages ? nbytes : 8);
+        const size_t fixed = tile_smem(F, 0, ilp * pair, nstages, d.top_stride);
         if (fixed >= budget) return 0;
         const int warp_cap = (pair == 4) ? 20 : (ilp == 8 ? 8 : 12);   // thread bound of dt_walk_tile (+1 producer warp)
         int g = (int)std::min<size_t>((size_t)(warp_cap / pair), (budget - fixed) / ((size_t)F * 128));
@@ -345,8 +300,7 @@ inline Plan make_plan(const Dev& d, const Tune& tune, int want) {
                 best = score;
                 staged.variant = KERNEL_TILE_STAGED;
                 staged.ilp = ilp; staged.pair = pair; staged.nstages = st; staged.nwarps = g * pair; staged.wide = d.wide;
-                staged.c16 = c16;
-                staged.smem = tile_smem(F, g, ilp * pair, st, d.top_stride, nbytes);
+                staged.smem = tile_smem(F, g, ilp * pair, st, d.top_stride);
             }
             if (tune.ilp && tune.stages && tune.pair) break;
         }
@@ -369,26 +323,24 @@ inline Plan make_plan(const Dev& d, const Tune& tune, int want) {
     return p;
 }
 
-// phased ring refill needs >= 3 staged levels and at most 4 ring stages (16 mbarriers in the header)
+// phased ring refill needs >= 3 staged levels and at most 4 ring stages (16 mbarriers in the header).
+// Measured (profiles/r01_summary.md): +7 % at D = 12 (64 KiB stage), -4 % at D <= 10 (<= 16 KiB stage, the
+// refill is already cheap there and the extra barrier hand-offs cost more than they hide).
 inline uint32_t phased_level(const Dev& d, const Tune& tune, const Plan& pl) {
-    if (pl.variant != KERNEL_TILE_STAGED || pl.nstages > 4) return 0xFFFFFFFFu;
-    return pl.c16 ? d.c16_Lw : phased_split(d.Dtop, tune);       // the compact layout was built around its split
+    if (pl.variant != KERNEL_TILE_STAGED) return 0xFFFFFFFFu;
+    const bool phased = tune.phased >= 1 || (tune.phased == -1 && d.Dtop >= 10);
+    // part A = levels 0..Lw; DTE_TUNE phased=k moves the split k-1 levels further up (smaller part A)
+    const uint32_t up = tune.phased > 1 ? (uint32_t)tune.phased - 1 : 0;
+    return (phased && d.Dtop >= 3 + up && pl.nstages <= 4) ? d.Dtop - 3 - up : 0xFFFFFFFFu;
 }
 
-template <int ILP, int P, bool STAGED, bool WIDE, int NT, bool C16>
-cudaError_t launch_tile_c(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
-    auto k = dt_walk_tile<ILP, P, STAGED, WIDE, NT, C16>;
+template <int ILP, int P, bool STAGED, bool WIDE, int NT>
+cudaError_t launch_tile_nt(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
+    auto k = dt_walk_tile<ILP, P, STAGED, WIDE, NT>;
     cudaError_t rc = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     k<<<grid, threads, smem, st>>>(wp);
     return cudaGetLastError();
-}
-template <int ILP, int P, bool STAGED, bool WIDE, int NT>
-cudaError_t launch_tile_nt(const WalkParams& wp, int grid, int threads, size_t smem, cudaStream_t st) {
-    if constexpr (STAGED) {
-        if (wp.top16) return launch_tile_c<ILP, P, STAGED, WIDE, NT, true>(wp, grid, threads, smem, st);
-    }
-    return launch_tile_c<ILP, P, STAGED, WIDE, NT, false>(wp, grid, threads, smem, st);
 }
 // thread-bound classes (see dt_walk_tile): <= 12 warps -> the 168-register instantiation, else the wide one
 template <int ILP, int P, bool STAGED, bool WIDE>
@@ -427,8 +379,6 @@ inline cudaError_t launch_walk(Dev& d, const Tune& tune, int want_variant, const
     wp.wide_rows = (wp.F % 8 == 0 && (reinterpret_cast<uintptr_t>(d_tuples) & 31u) == 0) ? 1u : 0u;
     wp.fill_split = tune.fill ? 1u : 0u;      // DTE_TUNE fill=1: one bulk copy per tree instead of one per stage
     wp.Lw = phased_level(d, tune, pl);
-    wp.top16 = pl.c16 ? d.d_top16 : nullptr;   // non-null selects the compact-top instantiation
-    wp.c16_nA = d.c16_nA;
     wp.tiles = 0;
     cudaError_t rc;
     if (pl.variant == KERNEL_GENERIC) {
@@ -471,8 +421,8 @@ inline void kernel_name(const Dev& d, const Tune& tune, int want, char* buf, siz
         snprintf(buf, len, "dt_walk_generic<%d>", pl.wide ? 1 : 0);
     } else {
         const bool staged = pl.variant == KERNEL_TILE_STAGED;
-        snprintf(buf, len, "dt_walk_tile<%d, %d, %d, %d, %d, %d> warps=%d stages=%d phased=%d threads=%d smem=%zu",
-                 pl.ilp, pl.pair, staged ? 1 : 0, pl.wide ? 1 : 0, pl.thread_bound(), pl.c16 ? 1 : 0, pl.nwarps, pl.nstages,
+        snprintf(buf, len, "dt_walk_tile<%d, %d, %d, %d, %d> warps=%d stages=%d phased=%d threads=%d smem=%zu",
+                 pl.ilp, pl.pair, staged ? 1 : 0, pl.wide ? 1 : 0, pl.thread_bound(), pl.nwarps, pl.nstages,
                  phased_level(d, tune, pl) != 0xFFFFFFFFu ? 1 : 0, pl.threads(), pl.smem);
     }
 }

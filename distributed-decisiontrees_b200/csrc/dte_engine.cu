@@ -183,10 +183,8 @@ void free_ensemble(Dev& d) {
     cudaSetDevice(d.ordinal);
     if (d.d_top) cudaFree(d.d_top);
     if (d.d_bottom) cudaFree(d.d_bottom);
-    if (d.d_top16) cudaFree(d.d_top16);
     d.d_top = nullptr;
     d.d_bottom = nullptr;
-    d.d_top16 = nullptr;
     d.T = d.Tpad = 0;
     d.ensemble_bytes = 0;
 }
@@ -199,21 +197,16 @@ int upload_ensemble(dte_engine* e, Dev& d, const PackedEnsemble& pk) {
     CUDA_TRY(e, cudaMalloc(&d.d_bottom, pk.bottom.size() * sizeof(uint4)));
     CUDA_TRY(e, cudaMemcpy(d.d_top, pk.top.data(), pk.top.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(d.d_bottom, pk.bottom.data(), pk.bottom.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-    if (!pk.top16.empty()) {
-        CUDA_TRY(e, cudaMalloc(&d.d_top16, pk.top16.size()));
-        CUDA_TRY(e, cudaMemcpy(d.d_top16, pk.top16.data(), pk.top16.size(), cudaMemcpyHostToDevice));
-    }
-    d.c16_nA = pk.c16_nA; d.c16_Lw = pk.c16_Lw;
     d.g = pk.g;
     d.T = pk.T; d.Tpad = pk.Tpad; d.Dtop = pk.Dtop; d.top_stride = pk.top_stride; d.nb = pk.nb; d.wide = pk.wide;
-    d.ensemble_bytes = pk.top.size() * sizeof(uint2) + pk.bottom.size() * sizeof(uint4) + pk.top16.size();
+    d.ensemble_bytes = pk.top.size() * sizeof(uint2) + pk.bottom.size() * sizeof(uint4);
     return DTE_OK;
 }
 
 int pack_or_fail(dte_engine* e, const Geom& g, const unsigned char* wl, size_t n_wl, const unsigned char* fl, size_t n_fl,
                  uint32_t first, uint32_t count, PackedEnsemble& pk) {
     std::string msg;
-    const int rc = pack_ensemble(g, wl, n_wl, fl, n_fl, first, count, pk, msg, e->tune);
+    const int rc = pack_ensemble(g, wl, n_wl, fl, n_fl, first, count, pk, msg);
     if (rc) return fail(e, rc == -4 ? DTE_ERR_UNSUPPORTED : DTE_ERR_ARG, "%s", msg.c_str());
     return DTE_OK;
 }
@@ -332,10 +325,7 @@ int ensure_slots(dte_engine* e, Dev& d, size_t cap, uint32_t F, bool parts) {
 }
 
 size_t default_chunk(const dte_engine* e, uint32_t F) {
-    // 64 MiB of tuples per landing buffer; a multi-device handle issues ~25 API calls per device per buffer from ONE
-    // host thread, so it takes up to 4 x larger buffers to stay walk-bound instead of launch-bound (measured, 8 GPUs)
-    const size_t bytes = (64ull << 20) * std::min<size_t>(4, e->devs.size());
-    size_t c = e->opt_chunk_tuples ? e->opt_chunk_tuples : (e->tune.chunk ? e->tune.chunk : std::max<size_t>(4096, bytes / (F * 4)));
+    size_t c = e->opt_chunk_tuples ? e->opt_chunk_tuples : (e->tune.chunk ? e->tune.chunk : std::max<size_t>(4096, (64ull << 20) / (F * 4)));
     return (std::max<size_t>(c, 4) + 3) & ~(size_t)3;      // whole result lines per slot
 }
 

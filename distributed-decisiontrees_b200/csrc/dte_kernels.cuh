@@ -55,8 +55,6 @@ struct WalkParams {
     uint32_t Lw;                // phased ring refill: level iteration at which part B is needed; 0xFFFFFFFF = off
     uint32_t accumulate;        // 1: scores[i] += partial with a system-scope reduction (fused cross-device combine)
     uint32_t wide_rows;         // 1: tuple rows are 32-byte aligned (F % 8 == 0, base aligned): 256-bit tile loads
-    const unsigned char* top16; // C16 kernels: [trees_padded][6 * top_stride] compact tops, see "compact tops" below
-    uint32_t c16_nA;            // C16: node slots in part A of a tree block (== top_stride when the refill is not phased)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -171,63 +169,6 @@ __device__ __forceinline__ uint32_t step_select(uint32_t x, uint32_t thr, uint32
         "selp.u32 %0, %6, %5, pr;\n\t"
         "}"
         : "=r"(r) : "r"(x), "r"(thr), "r"(missing), "r"(meta), "r"(a_left), "r"(a_right));
-    return r;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Compact tops (C16): 6 bytes per node instead of 8, so the node read is ONE 32-bit shared-memory access.
-//   node32 = (thr & 0xFFFF0000) | missing_right << 15 | fidx        lo16 = thr & 0xFFFF   (separate array)
-// The comparator is a signed compare of the raw 32-bit words (DTPU.sv:655).  Whenever the HIGH halves of feature
-// and threshold differ, comparing the feature with node32 itself gives the exact answer (the low half cannot
-// change the outcome); only when they are equal (hi16(x) == hi16(thr): ~0.3 % of visits on U[0,1) data) is the low
-// half of the threshold fetched — a predicated 16-bit load from the lo16 array — and the full 32-bit threshold
-// rebuilt.  Decisions are therefore bit-exact for ANY data; the rare path only costs a little time.
-// One tree block in global memory and in the ring (nA = slots of part A, nB = top_stride - nA):
-//   [A32: nA x 4 B][Alo: nA x 2 B][B32: nB x 4 B][Blo: nB x 2 B]      part A = levels 0..Lw, part B = the rest
-// so each part of the phased ring refill is still ONE contiguous bulk copy per tree.
-// ---------------------------------------------------------------------------------------------
-#ifndef DTE_C16_BRANCH
-#define DTE_C16_BRANCH 0     // 1: warp-vote + branch around the rare low-half fetch instead of predication
-#endif
-__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t step_select16(uint32_t x, uint32_t nd, uint32_t missing, uint32_t lo_addr,
-                                                  uint32_t a_left, uint32_t a_right) {
-    uint32_t r, thr = nd;
-#if DTE_C16_BRANCH
-    // the high halves tie in some lane of the warp (rare): fetch the low half of the threshold there
-    if (__any_sync(0xFFFFFFFFu, (x ^ nd) < 0x10000u)) {
-        if ((x ^ nd) < 0x10000u) thr = __byte_perm(lds16(lo_addr), nd, 0x7610);
-    }
-#else
-    asm volatile("{\n\t"
-        ".reg .pred pa;\n\t"
-        ".reg .b32 t, lo;\n\t"
-        "xor.b32 t, %1, %2;\n\t"
-        "setp.lt.u32 pa, t, 65536;\n\t"          // high halves equal: the low half of the threshold decides
-        "mov.b32 lo, 0;\n\t"
-        "@pa ld.shared.u16 lo, [%3];\n\t"
-        "@pa prmt.b32 %0, lo, %2, 0x7610;\n\t"    // thr = hi16(node32) : lo16
-        "}"
-        : "+r"(thr) : "r"(x), "r"(nd), "r"(lo_addr) : "memory");
-#endif
-    asm("{\n\t"
-        ".reg .pred pge, pm, pmr, t1, t2, npm, pr;\n\t"
-        ".reg .b32 t;\n\t"
-        "setp.ge.s32 pge, %1, %2;\n\t"            // !(x < thr), signed compare of the raw words (DTPU.sv:655)
-        "setp.eq.u32 pm, %1, %3;\n\t"             // feature == missing pattern (DTPU.sv:653)
-        "and.b32 t, %4, 32768;\n\t"
-        "setp.ne.u32 pmr, t, 0;\n\t"              // missing goes right (DTPU.sv:659)
-        "and.pred t1, pm, pmr;\n\t"
-        "not.pred npm, pm;\n\t"
-        "and.pred t2, npm, pge;\n\t"
-        "or.pred pr, t1, t2;\n\t"
-        "selp.u32 %0, %6, %5, pr;\n\t"
-        "}"
-        : "=r"(r) : "r"(x), "r"(thr), "r"(missing), "r"(nd), "r"(a_left), "r"(a_right));
     return r;
 }
 
@@ -373,9 +314,8 @@ __device__ __forceinline__ void group_barrier(uint32_t id, uint32_t nthreads) {
 // NT = thread bound of the instantiation.  Registers are allocated per SM sub-partition (16 K each), so the
 // per-thread limit is set by ceil(warps / 4): 9..12 warps -> 168 registers, 13..16 warps -> 128.  The planner
 // picks the 384-thread instantiation whenever the plan fits in 12 warps (cfg3: 5 tuple groups x 2 + producer).
-template <int ILP, int P, bool STAGED, bool WIDE, int NT, bool C16 = false>
+template <int ILP, int P, bool STAGED, bool WIDE, int NT>
 __global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
-    static_assert(!C16 || STAGED, "compact tops exist only in the staged ring");
     static_assert(ILP * P == 8 || ILP * P == 4, "a step covers a tree8 group or half of one");
     constexpr int BV = WIDE ? 4 : 2;
     constexpr int SP = ILP * P;                         // trees per ring stage / per step
@@ -384,7 +324,7 @@ __global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t G = p.nwarps / P;                    // tuple groups per CTA
     const uint32_t M = 32u * G;
-    const uint32_t tree_bytes = p.top_stride * (C16 ? 6u : 8u);
+    const uint32_t tree_bytes = p.top_stride * 8u;
     const uint32_t stage_bytes = (uint32_t)SP * tree_bytes;
     const uint32_t ring_bytes = STAGED ? p.nstages * stage_bytes : 0u;
     const uint32_t xs_base = sbase + kHdrBytes + ring_bytes;
@@ -407,7 +347,7 @@ __global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
             // ---------------- producer: stream tree tops through the ring ----------------
             if (lane == 0) {
                 const uint64_t total = (uint64_t)my_tiles * steps;
-                const char* src0 = C16 ? reinterpret_cast<const char*>(p.top16) : reinterpret_cast<const char*>(p.top);
+                const char* src0 = reinterpret_cast<const char*>(p.top);
                 uint32_t slot = 0, par = 1;                          // fresh barrier: parity-1 wait passes
                 uint32_t q = 0;
                 // Phased refill (p.Lw set): a stage is refilled in two parts with their own barriers.
@@ -417,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
                 //   ONE stage overlaps copy and walk: B of step q+1 streams in under levels 0..Lw of step q+1,
                 //   A of step q+1 under the last level + bottom records + leaf sums of step q.
                 const bool phased = p.Lw != 0xFFFFFFFFu;
-                const uint32_t bytesA = phased ? ((C16 ? 12u : 16u) << p.Lw) : tree_bytes;
+                const uint32_t bytesA = phased ? (16u << p.Lw) : tree_bytes;
                 const uint32_t bytesB = tree_bytes - bytesA;
                 for (uint64_t it = 0; it < total; ++it) {
                     const uint32_t dst = sbase + kHdrBytes + slot * stage_bytes;
@@ -564,66 +504,7 @@ __global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
             uint32_t o[ILP];
 #pragma unroll
             for (int c = 0; c < ILP; ++c) o[c] = 0;
-            if constexpr (C16) {
-                // ---- compact tops: LDS.32 node, low half of the threshold only when the high halves tie ----
-                mbar_wait(sbase + 8 * slot, par);
-                const uint32_t tb = sbase + kHdrBytes + slot * stage_bytes + sub * ILP * tree_bytes;
-                const bool phased = p.Lw != 0xFFFFFFFFu;
-                const uint32_t nA = p.c16_nA, nB = p.top_stride - nA;
-                // node n of part A sits at base + 4n, its low half at base + 4nA + 2n; node n of part B at
-                // vb + 4n with vb = base + 2nA + 4, its low half at base + 6nA + 4nB + 2(n - nA + 1).  With A = the
-                // node's address the child is A' = 2A + kb + 4*right, kb = 4 - base inside A, 2nA + 8 - base when
-                // the child is the first level of B, -base - 2nA inside B; the low half is at (A >> 1) + clo.
-                uint32_t A[ILP], kb[ILP], clo[ILP];
-#pragma unroll
-                for (int c = 0; c < ILP; ++c) {
-                    const uint32_t base = tb + c * tree_bytes;
-                    A[c] = base; kb[c] = 4u - base; clo[c] = (base >> 1) + 4u * nA;
-                }
-                const uint32_t d1 = 2u * nA + 4u, d2 = 0u - 4u * nA - 8u, dlo = 4u * nB - nA;
-                constexpr int H = ILP / 2;
-                uint32_t nd[ILP], xv[ILP];
-                auto S1 = [&](int c) { nd[c] = lds32(A[c]); };
-                auto S2 = [&](int c) { xv[c] = feat(nd[c] & 0x7FFu); };
-                auto S3 = [&](int c) {
-                    const uint32_t a2 = A[c] + A[c] + kb[c];
-                    A[c] = step_select16(xv[c], nd[c], p.missing, (A[c] >> 1) + clo[c], a2, a2 + 4u);
-                };
-#pragma unroll
-                for (int c = 0; c < ILP; ++c) S1(c);
-#pragma unroll
-                for (int c = 0; c < H; ++c) S2(c);
-                for (uint32_t lvl = 0; lvl + 1 < p.Dtop; ++lvl) {
-                    if (phased) {
-                        if (lvl == p.Lw) {
-                            mbar_wait(sbase + 8 * (2 * p.nstages + slot), par);          // part B landed
-#pragma unroll
-                            for (int c = 0; c < ILP; ++c) kb[c] += d1;                    // children of level Lw live in part B
-                        } else if (lvl == p.Lw + 1) {
-#pragma unroll
-                            for (int c = 0; c < ILP; ++c) { kb[c] += d2; clo[c] += dlo; }
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < H; ++k) { S3(k); S1(k); S2(k + H); }
-#pragma unroll
-                    for (int k = H; k < ILP; ++k) { S3(k); S1(k); S2(k - H); }
-                }
-                if (phased) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(sbase + 8 * (p.nstages + slot));
-                }
-#pragma unroll
-                for (int k = 0; k < H; ++k) { S3(k); S2(k + H); }
-#pragma unroll
-                for (int k = H; k < ILP; ++k) S3(k);
-#pragma unroll
-                for (int c = 0; c < ILP; ++c)                                             // node INDEX of the level below the top
-                    o[c] = (A[c] - (tb + c * tree_bytes + (phased ? 2u * nA + 4u : 0u))) >> 2;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sbase + 8 * ((phased ? 3 * p.nstages : p.nstages) + slot));
-                if (++slot == p.nstages) { slot = 0; par ^= 1; }
-            } else if (STAGED) {
+            if (STAGED) {
                 mbar_wait(sbase + 8 * slot, par);
                 const uint32_t tb = sbase + kHdrBytes + slot * stage_bytes + sub * ILP * tree_bytes;
                 // Absolute shared-memory addresses: with A = tb_c + o the child address is
@@ -690,7 +571,7 @@ __global__ void __launch_bounds__(NT, 1) dt_walk_tile(const WalkParams p) {
             // bottom: last two comparison levels + leaves, ONE 32 B (64 B) record per walk
 #pragma unroll
             for (int c = 0; c < ILP; ++c) {
-                const uint32_t j = (C16 ? o[c] : (o[c] >> 3)) - (p.nb - 1);
+                const uint32_t j = (o[c] >> 3) - (p.nb - 1);
                 bot_load(dst[c], p.bottom + ((size_t)(t0 + c) * p.nb + j) * BV);
             }
         };

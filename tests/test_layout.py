@@ -1,4 +1,3 @@
-import os
 """Host-side layout logic: stream packing, synthetic generators, sharding arithmetic."""
 import numpy as np
 
@@ -107,18 +106,9 @@ def test_repacker_on_the_cpu_against_the_oracle(tmp_path):
         wl, fl = L.pack_streams(W, FI, D)
         for name, arr in (("w", wl), ("f", fl), ("x", x)):
             np.ascontiguousarray(arr).tofile(tmp_path / (name + ".bin"))
-        # thresholds that TIE with features in the high 16 bits: the compact 6-byte tops must fetch the low half
-        if D >= 5:
-            for t in range(T):
-                for i in range(0, n_int, 3):
-                    W[t, i] = (x[(t + i) % 97, FI[t, i] & 0x7FF] & 0xFFFF0000) | int(rng.integers(0, 1 << 16))
-            wl, fl = L.pack_streams(W, FI, D)
-            np.ascontiguousarray(wl).tofile(tmp_path / "w.bin")
-        for tune in ("", "phased=1", "phased=2", "phased=0"):
-            env = dict(os.environ, DTE_TUNE=tune)
-            out = subprocess.run([exe, str(D), str(F), str(T), "97", str(L.MISSING_DEFAULT), str(tmp_path / "w.bin"), str(tmp_path / "f.bin"),
-                                  str(tmp_path / "x.bin")], capture_output=True, timeout=120, env=env)
-            assert out.returncode == 0, (tune, out.stderr)
+        out = subprocess.run([exe, str(D), str(F), str(T), "97", str(L.MISSING_DEFAULT), str(tmp_path / "w.bin"), str(tmp_path / "f.bin"),
+                              str(tmp_path / "x.bin")], capture_output=True, timeout=120)
+        assert out.returncode == 0, out.stderr
         got = np.frombuffer(out.stdout, dtype=np.uint32).reshape(97, T)
         cfg = oracle_cfg(D, 1, 1, L.MISSING_DEFAULT, F, T)
         w_cls, f_cls = L.tree_cls(D)

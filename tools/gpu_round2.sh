@@ -12,20 +12,6 @@ case "$stage" in
   ref)      timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference rc=$?"; cut -c1-300 gpurun_out/bench_reference.json ;;
   multitests) timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_parity.py -m gpu -q -k "multi or ring or early or kats or cpp_host or queue or stream" 2>&1 | tee gpurun_out/pytest_gpu_multi.log | tail -15 ;;
   benchN)   N=${DTE_N:-2}; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --tuples ${DTE_TUPLES:-8000000} --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench$N rc=$?"; cut -c1-300 gpurun_out/bench_${N}gpu.json; tail -3 gpurun_out/bench_${N}gpu.err ;;
-  c16)      DTE_C16=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tee gpurun_out/pytest_gpu_c16.log | tail -6
-            Q="--tuples 8000000 --steps 5 --warmup 3 --no-cpu --no-extras --e2e-tuples 500000"
-            for cfg in "0|" "1|" "1|pair=2,ilp=2,stages=1" "1|pair=2,ilp=2,stages=2" "1|pair=2,ilp=4,stages=1,phased=2" "1|pair=1,ilp=8,stages=1" "1|pair=4,stages=1" "1|pair=2,ilp=4,stages=1,phased=0"; do
-              c=${cfg%%|*}; t=${cfg#*|}
-              DTE_C16=$c DTE_TUNE="$t" timeout 300 python bench.py $Q > gpurun_out/c16_tmp.json 2> gpurun_out/c16_tmp.err
-              python - "$c" "$t" <<'PY'
-import json, sys
-try:
-    d = json.load(open("gpurun_out/c16_tmp.json"))
-    print("c16=%s tune=%-34s %7.2f M tuples/s  %s" % (sys.argv[1], sys.argv[2], d["value"] / 1e6, d["config"]["kernel"]))
-except Exception as e:
-    print("c16=%s tune=%s failed: %s" % (sys.argv[1], sys.argv[2], e)); print(open("gpurun_out/c16_tmp.err").read()[-600:])
-PY
-            done | tee gpurun_out/c16_sweep.txt ;;
   micro)    timeout 300 tools/pipe_microbench > gpurun_out/pipe_microbench.json 2> gpurun_out/pipe_microbench.err; echo "micro rc=$?"; cat gpurun_out/pipe_microbench.json ;;
   launches) B="--tuples 2000000 --steps 2 --warmup 1 --no-cpu --e2e-tuples 200000 --no-extras"
             timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py $B > gpurun_out/launches_bench.log 2>&1; echo "ncu launches rc=$?" ;;

@@ -29,9 +29,7 @@ int main(int argc, char** argv) {
     auto wl = slurp(argv[6]), fl = slurp(argv[7]), xs = slurp(argv[8]);
     PackedEnsemble pk;
     std::string msg;
-    Tune tune;
-    parse_tune(tune);                 // DTE_TUNE phased=k chooses the split of the compact layout
-    int rc = pack_ensemble(g, wl.data(), wl.size() / 16, fl.data(), fl.size() / 16, 0, 0, pk, msg, tune);
+    int rc = pack_ensemble(g, wl.data(), wl.size() / 16, fl.data(), fl.size() / 16, 0, 0, pk, msg);
     if (rc) { fprintf(stderr, "pack_ensemble: %d %s\n", rc, msg.c_str()); return 3; }
     if (pk.T != T) return 4;
     const uint32_t* X = reinterpret_cast<const uint32_t*>(xs.data());
@@ -50,30 +48,7 @@ int main(int argc, char** argv) {
                 if (xv == g.missing) inc = nd.y >> 16;
                 o = 2 * o + inc;
             }
-            uint32_t j = (o >> 3) - (pk.nb - 1);
-            if (!pk.top16.empty()) {
-                // the compact tops, decoded with the C16 kernel's own address arithmetic on a byte image of the tree
-                // block placed at an arbitrary even "shared-memory address" (dte_kernels.cuh, walk_top<C16>)
-                const unsigned char* blk = pk.top16.data() + (size_t)t * pk.top_stride * 6;
-                const uint32_t base = 0x1230u, nA = pk.c16_nA, nB = pk.top_stride - nA;
-                const bool phased = pk.c16_Lw != 0xFFFFFFFFu;
-                auto ld32 = [&](uint32_t a) { uint32_t v; memcpy(&v, blk + (a - base), 4); return v; };
-                auto ld16 = [&](uint32_t a) { uint16_t v; memcpy(&v, blk + (a - base), 2); return (uint32_t)v; };
-                uint32_t A = base, kb = 4u - base, clo = (base >> 1) + 4u * nA;
-                const uint32_t d1 = 2u * nA + 4u, d2 = 0u - 4u * nA - 8u, dlo = 4u * nB - nA;
-                for (uint32_t lvl = 0; lvl < pk.Dtop; ++lvl) {
-                    if (phased && lvl == pk.c16_Lw) kb += d1;
-                    else if (phased && lvl == pk.c16_Lw + 1) { kb += d2; clo += dlo; }
-                    const uint32_t nd = ld32(A);
-                    const uint32_t xv = x[nd & 0x7FFu];
-                    uint32_t thr = nd;
-                    if ((xv ^ nd) < 0x10000u) thr = (nd & 0xFFFF0000u) | ld16((A >> 1) + clo);
-                    const bool right = (xv == g.missing) ? ((nd & 0x8000u) != 0) : !((int32_t)xv < (int32_t)thr);
-                    A = A + A + kb + (right ? 4u : 0u);
-                }
-                const uint32_t j16 = ((A - (base + (phased ? 2u * nA + 4u : 0u))) >> 2) - (pk.nb - 1);
-                if (j16 != j) { fprintf(stderr, "compact tops disagree: tuple %zu tree %u: %u vs %u\n", i, t, j16, j); return 5; }
-            }
+            const uint32_t j = (o >> 3) - (pk.nb - 1);
             const uint4* rec = pk.bottom.data() + ((size_t)t * pk.nb + j) * BV;
             uint32_t fp, fl_, fr, mp, ml, mr; uint4 leaves;
             if (pk.wide) {
