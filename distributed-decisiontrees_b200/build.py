@@ -11,7 +11,7 @@ OUT = os.path.join(HERE, "libdte.so")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl", "-lpthread",
 ]
 
 

@@ -13,9 +13,12 @@
 #include "../../include/dte.h"
 #include "dte_device.cuh"
 
+#include <atomic>
 #include <chrono>
 #include <dlfcn.h>
+#include <mutex>
 #include <new>
+#include <thread>
 
 using namespace dte;
 
@@ -97,7 +100,9 @@ struct dte_engine {
 
     // ---- cumulative counters (cluster counters are only cleared by a hardware reset, DTPUCluster.sv:85-97) ----
     uint64_t cum_c0 = 0, cum_c0_lines = 0;
-    uint64_t tuples_in = 0, tuples_out = 0;
+    uint64_t tuples_in = 0;
+    std::atomic<uint64_t> tuples_out{0};
+    std::mutex err_mu;                // fail() may be reached from the per-device feeder threads of infer_host
 
     // ---- timing: progCycles / execCycles (DTInference.sv:330-357) ----
     Clock::time_point t_start, t_prog0, t_prog1, t_done;
@@ -120,6 +125,7 @@ int fail(dte_engine* e, int code, const char* fmt, ...) {
         va_start(ap, fmt);
         vsnprintf(buf, sizeof buf, fmt, ap);
         va_end(ap);
+        std::lock_guard<std::mutex> lk(e->err_mu);
         e->err = buf;
     }
     return code;
@@ -709,18 +715,34 @@ int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_
         for (Dev& d : e->devs)
             if (d.slot[d.cur].fill) advance_slot(d);
     } else {
+        // chunks round-robin over the devices; with several devices each one is fed by its own host thread (one
+        // thread cannot issue the ~25 runtime calls per chunk fast enough for 8 PCIe links)
         const size_t chunk = e->devs[0].cap_tuples, G = e->devs.size();
-        size_t i = 0;
-        for (size_t off = 0; off < n && !rc; off += chunk, ++i) {
-            Dev& d = e->devs[i % G];
-            const size_t cnt = std::min(chunk, n - off);
-            d.sink_sc = h_scores + off;
-            d.sink_lb = h_labels ? h_labels + off : nullptr;
-            rc = land_dev(e, d, h_tuples + off * tb, cnt * tb);
-            if (!rc && d.slot[d.cur].fill) {         // a short last chunk
-                rc = submit_dev(e, d, d.cur);
-                advance_slot(d);
+        auto feed = [&](size_t g) -> int {
+            Dev& d = e->devs[g];
+            int r = DTE_OK;
+            size_t i = g;
+            for (size_t off = g * chunk; off < n && !r; off += G * chunk, i += G) {
+                const size_t cnt = std::min(chunk, n - off);
+                d.sink_sc = h_scores + off;
+                d.sink_lb = h_labels ? h_labels + off : nullptr;
+                r = land_dev(e, d, h_tuples + off * tb, cnt * tb);
+                if (!r && d.slot[d.cur].fill) {          // a short last chunk
+                    r = submit_dev(e, d, d.cur);
+                    advance_slot(d);
+                }
             }
+            return r;
+        };
+        if (G == 1) {
+            rc = feed(0);
+        } else {
+            std::vector<int> rcs(G, DTE_OK);
+            std::vector<std::thread> th;
+            for (size_t g = 1; g < G; ++g) th.emplace_back([&, g] { rcs[g] = feed(g); });
+            rcs[0] = feed(0);
+            for (auto& t : th) t.join();
+            for (int r : rcs) if (r && !rc) rc = r;
         }
     }
     for (Dev& d : e->devs) {

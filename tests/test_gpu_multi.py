@@ -291,3 +291,30 @@ def test_cpp_host_drives_the_whole_ring(devs):
             r = json.loads(out.stdout.strip().splitlines()[-1])
             assert r["gpus"] == G and r["partition"] == part
             assert r["results"] == n and r["score_words_sum"] == int(want.astype(np.uint64).sum()), (part, mode, r)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("devs", [d for d in DEVICE_LISTS if len(set(d)) == len(d)], ids=lambda d: "gpus" + "".join(map(str, d)))
+def test_nccl_combine_option(devs):
+    """DTE_OPT_COMBINE = 1: the partial scores are summed by ONE ncclReduce (libnccl dlopen'ed by libdte.so) instead of
+    the ring-order kernel — north_star's wording; the order is NCCL's, so 1e-5 relative (2 devices: a + b is commutative,
+    still bit-exact), labels stable."""
+    G = len(devs)
+    T, D, F, K, n = 16 * G, 6, 64, 2, 20_011
+    W, FI, x, wl, fl, _ = _case(T, D, F, n, 131)
+    want, _ = _ensemble_reference(W, FI, x, D, K, G)
+    with ddt.Engine(devs) as e:
+        e.set_option(E.DTE_OPT_COMBINE, 1)
+        e.set_option(E.DTE_OPT_CHUNK_TUPLES, 4096)
+        _write_regs(e, multi_node_regs(T, D, F, K, n, G, "ensemble"))
+        e.load_ensemble(wl, fl)
+        sc, lb = e.infer_host(x)
+        if G == 2:
+            assert (sc.view(np.uint32) == want).all()
+        else:
+            assert np.allclose(sc, want.view(np.float32), rtol=1e-5, atol=1e-7)
+        assert (lb == O.labels(sc.view(np.uint32))).all()
+        assert (lb == O.labels(want)).mean() > 0.999
+        e.set_option(E.DTE_OPT_COMBINE, 0)                      # back to the ring kernel on the same handle: bit-exact
+        sc2, lb2 = e.infer_host(x)
+        assert (sc2.view(np.uint32) == want).all() and (lb2 == O.labels(want)).all()
