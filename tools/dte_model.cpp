@@ -17,7 +17,7 @@ int main(int argc, char** argv) {
     const int G = argc > 4 ? atoi(argv[4]) : 1;
 
     // ---- B200 constants (measured, round 1) ----
-    const double visits_per_s = 96.6e6 * 1024 * 12;      // node visits/s per GPU at cfg3 (dt_walk_tile<4,2,1,0>)
+    const double visits_per_s = 102.8e6 * 1024 * 12;     // node visits/s per GPU at cfg3 (dt_walk_tile<4,2,1,0,384>, profiles/r02_summary.md)
     const double pcie_Bps = 54.5e9;                       // host->device through dte_infer_host, pinned
     const double hbm_Bps = 6585.4e9;                      // MEASURED_PEAKS.json
     const double nvlink_Bps = 725e9;                      // 8-rank all-reduce bus bandwidth (B200_PROFILING.md)
