@@ -1483,6 +1483,61 @@ int dte_kernel_name(dte_t* e, char* buf, size_t len) {
     return DTE_OK;
 }
 
+int dte_autotune(dte_t* e, size_t n_tuples, char* report, size_t report_len) {
+    if (!e) return DTE_ERR_ARG;
+    Dev& d = e->devs[0];
+    if (!d.d_top) return fail(e, DTE_ERR_STATE, "no ensemble loaded");
+    Geom g;
+    TRY(decode_geom(e, g));
+    TRY(check_resident(e, g));
+    TRY(drain_all(e));
+    const uint32_t F = d.g.F();
+    n_tuples = std::max<size_t>(n_tuples, (size_t)d.sm_count * 192 * 4);
+    CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    void* d_x = nullptr;
+    float* d_s = nullptr;
+    CUDA_TRY(e, cudaMalloc(&d_x, n_tuples * F * 4));
+    if (cudaMalloc(&d_s, n_tuples * 4) != cudaSuccess) { cudaFree(d_x); return fail(e, DTE_ERR_NOMEM, "autotune: out of device memory"); }
+    synth_tuples_kernel<<<(unsigned)d.sm_count * 8, 256, 0, d.s_main>>>(static_cast<uint32_t*>(d_x), 0, (unsigned long long)n_tuples * F, 0x7091E5ull, 10000u, d.g.missing);
+    struct Cand { int ilp, pair, stages, phased; };
+    const Cand cands[] = {{4, 2, 1, 1}, {4, 2, 1, 0}, {2, 4, 1, 1}, {2, 4, 1, 0}, {8, 1, 1, 0}, {8, 1, 2, 0}, {4, 1, 2, 0}, {2, 2, 2, 0}, {2, 2, 1, 0}};
+    const Tune saved = e->tune;
+    Tune best = saved;
+    float best_ms = 1e30f;
+    std::string rep;
+    char name[256], line[400];
+    int rc = DTE_OK;
+    for (const Cand& c : cands) {
+        Tune t = saved;
+        t.ilp = c.ilp; t.pair = c.pair; t.stages = c.stages; t.phased = c.phased;
+        const Plan pl = make_plan(d, t, KERNEL_AUTO);
+        if (pl.variant != KERNEL_TILE_STAGED || pl.ilp != c.ilp || pl.pair != c.pair || pl.nstages != c.stages) continue;   // does not fit
+        if (c.phased && phased_level(d, t, pl) == 0xFFFFFFFFu) continue;
+        float ms = 0;
+        for (int rep_i = 0; rep_i < 2 && !rc; ++rep_i) {                     // the second launch is the measurement
+            const char* why = nullptr;
+            cudaEventRecord(d.ev_t0, d.s_main);
+            cudaError_t st = launch_walk(d, t, KERNEL_AUTO, d_x, n_tuples, d_s, nullptr, d.s_main, false, &why);
+            cudaEventRecord(d.ev_t1, d.s_main);
+            if (st != cudaSuccess || cudaEventSynchronize(d.ev_t1) != cudaSuccess) { rc = fail(e, DTE_ERR_CUDA, "autotune launch failed: %s", cudaGetErrorString(st)); break; }
+            cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1);
+        }
+        if (rc) break;
+        kernel_name(d, t, KERNEL_AUTO, name, sizeof name);
+        snprintf(line, sizeof line, "%8.3f ms  %7.2f M tuples/s  %s\n", ms, n_tuples / (ms * 1e3), name);
+        rep += line;
+        if (ms < best_ms) { best_ms = ms; best = t; }
+    }
+    cudaFree(d_x);
+    cudaFree(d_s);
+    if (rc) { e->tune = saved; return rc; }
+    e->tune = best;
+    kernel_name(d, e->tune, e->forced_variant, name, sizeof name);
+    rep += std::string("chosen: ") + name + "\n";
+    if (report && report_len) snprintf(report, report_len, "%s", rep.c_str());
+    return DTE_OK;
+}
+
 int dte_set_node(dte_t* e, uint32_t node_index) {
     if (!e || node_index >= (uint32_t)kMaxRing) return DTE_ERR_ARG;            // devices_list has 20 entries (EngineCSR.sv:250-296)
     if (e->multi()) return fail(e, DTE_ERR_STATE, "a multi-device handle owns every ring position");

@@ -48,6 +48,7 @@ ABI = [
     ("dte_get_info", C.c_int, [C.c_void_p, C.c_void_p]),
     ("dte_set_kernel_variant", C.c_int, [C.c_void_p, C.c_int]),
     ("dte_kernel_name", C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    ("dte_autotune", C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("dte_set_node", C.c_int, [C.c_void_p, C.c_uint32]),
     ("dte_synth_tuples_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64,
                                            C.c_uint32, C.c_uint32, C.c_void_p]),
@@ -323,6 +324,12 @@ class Engine:
 
     def set_kernel_variant(self, variant):
         self._check(self._lib.dte_set_kernel_variant(self._h, int(variant)))
+
+    def autotune(self, n_tuples=0):
+        """Time the planner's alternatives on synthetic tuples and pin the fastest; returns the report text."""
+        buf = C.create_string_buffer(4096)
+        self._check(self._lib.dte_autotune(self._h, int(n_tuples), buf, 4096))
+        return buf.value.decode()
 
     def kernel_name(self):
         buf = C.create_string_buffer(256)

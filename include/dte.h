@@ -215,6 +215,12 @@ int dte_get_info(dte_t* engine, dte_info* info);
  * trees per warp, warps per tuple group, staged ring, wide records, thread bound). */
 int dte_kernel_name(dte_t* engine, char* buf, size_t len);
 
+/* Measure instead of guessing: times the planner's alternative launch plans (trees per warp x warps per tuple group x
+ * ring stages x phased refill) of the resident ensemble on n_tuples synthetic tuples and pins the fastest for this
+ * handle (every plan is bit-exact; only the speed differs).  The built-in choice is the plan measured best on the
+ * BASELINE geometries; call this for other (trees, levels, features).  `report` (may be NULL) receives one line per plan. */
+int dte_autotune(dte_t* engine, size_t n_tuples, char* report, size_t report_len);
+
 typedef enum {
     DTE_KERNEL_AUTO = 0,
     DTE_KERNEL_GENERIC = 1,    /* one thread per tuple, everything from global memory (any F, any D) */

@@ -521,3 +521,21 @@ def test_early_leaves_random_ensembles():
                     lo, hi = 2 * lo + 1, 2 * hi + 2
         x = L.synth_tuples(0, 777, F, seed=1500 + D, missing_ppm=20000)
         check_case(W, FI, x, D, 2, -(-T // 16))
+
+
+def test_autotune_picks_a_plan_and_stays_bit_exact():
+    """dte_autotune times the planner's alternatives on the resident ensemble and pins the fastest; whatever it picks,
+    scores stay the oracle's words (the built-in plan choice is a fitted heuristic)."""
+    for T, D, F in [(64, 9, 64), (32, 12, 256), (40, 7, 512)]:
+        W, FI = L.synth_ensemble(T, D, F, seed=700 + D)
+        x = L.synth_tuples(0, 3000, F, seed=701 + D)
+        wl, fl = L.pack_streams(W, FI, D)
+        want = O.scores(oracle_cfg(D, 8, -(-T // 64), L.MISSING_DEFAULT, F, T), wl, fl, x, threads=8)
+        with make_engine(T, D, F, 8, -(-T // 64)) as e:
+            e.load_ensemble(wl, fl)
+            before = e.kernel_name()
+            rep = e.autotune(200_000)
+            assert "chosen: dt_walk_tile<" in rep and rep.count("M tuples/s") >= 3, rep
+            assert e.kernel_name() in rep
+            got, lab = run_engine_host(e, x, E.DTE_KERNEL_AUTO)
+            assert (got == want).all() and (lab == O.labels(want)).all(), (before, rep)

@@ -94,23 +94,26 @@ int main(int argc, char** argv) {
             fl[(size_t)t * f_cls * 8 + i] = (uint16_t)((z % F) | (((z >> 33) & 1) << 13));
         }
     }
-    std::vector<uint32_t> x((size_t)N_tuples * F);
+    // DMA buffers from the "driver" (page-locked, every device of the handle can reach them at full PCIe speed)
+    uint32_t* x = nullptr;
+    float* scores = nullptr;
+    CHECK(dte_host_alloc(e, (size_t)N_tuples * F * 4, reinterpret_cast<void**>(&x)));
+    CHECK(dte_host_alloc(e, ((size_t)N_tuples + 4) * 4, reinterpret_cast<void**>(&scores)));
     for (uint64_t i = 0; i < (uint64_t)N_tuples * F; ++i) {
         uint64_t z = splitmix64(seed_t, i);
         x[i] = ((uint32_t)(z & 0xFFFFFFFFull) % 1000000u < 10000u) ? missing : fbits(u01(z));
     }
-
-    std::vector<float> scores((size_t)N_tuples, 0.0f);
+    memset(scores, 0, ((size_t)N_tuples + 4) * 4);
     auto t0 = std::chrono::steady_clock::now();
     if (stream_mode) {
         CHECK(dte_softreg_write(e, 200, 1));                                       // start
         CHECK(dte_stream_write(e, wl.data(), wl.size() / 4));                      // all weight lines
         CHECK(dte_stream_write(e, fl.data(), fl.size() / 8));                      // all feature-index lines
         t0 = std::chrono::steady_clock::now();
-        CHECK(dte_stream_write(e, x.data(), x.size() / 4));                        // tuple lines
+        CHECK(dte_stream_write(e, x, (size_t)N_tuples * F / 4));                   // tuple lines
         size_t got = 0, total = 0;
         do {
-            CHECK(dte_stream_read(e, scores.data() + total * 4, N_tuples / 4 - total, &got));
+            CHECK(dte_stream_read(e, scores + total * 4, N_tuples / 4 - total, &got));
             total += got;
         } while (got && total < N_tuples / 4);
         int done = 0;
@@ -119,7 +122,7 @@ int main(int argc, char** argv) {
     } else {
         CHECK(dte_load_ensemble(e, wl.data(), wl.size() / 4, fl.data(), fl.size() / 8, 0, 0));
         t0 = std::chrono::steady_clock::now();
-        CHECK(dte_infer_host(e, x.data(), N_tuples, scores.data(), nullptr));
+        CHECK(dte_infer_host(e, x, N_tuples, scores, nullptr));
     }
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     uint64_t sum = 0;
@@ -133,6 +136,8 @@ int main(int argc, char** argv) {
            N_trees, D, Size_tuple_Bytes, (unsigned long long)N_tuples, stream_mode ? "stream" : "host", G,
            G == 1 ? "single" : (ensemble_part ? "ensemble" : "data"), N_tuples / dt,
            (unsigned long long)exec_ns, (unsigned long long)sum, (unsigned long long)n_out);
+    dte_host_free(e, x);
+    dte_host_free(e, scores);
     dte_destroy(e);
     return 0;
 }
