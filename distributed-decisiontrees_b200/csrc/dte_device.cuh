@@ -257,6 +257,12 @@ struct Dev {
     std::deque<Pending> pend;
     std::vector<cudaEvent_t> ev_pool;
 
+    // pageable sources: a small pinned staging ring filled by a few copy threads, DMA'd from there (the driver's own
+    // pageable path stages through one thread and reaches ~10 GB/s; PCIe Gen5 takes 55)
+    unsigned char* h_stage[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};
+    int stage_next = 0;
+
     uint64_t kernel_launches = 0;
     double last_walk_ms = 0;
     uint64_t tuples_landed = 0;       // whole tuples landed on this device since `start`

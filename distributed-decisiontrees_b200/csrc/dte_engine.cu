@@ -422,6 +422,55 @@ int submit_dev(dte_engine* e, Dev& d, int b) {
     return DTE_OK;
 }
 
+// ---- host -> device copy of one piece of the stream ------------------------------------------------------
+constexpr size_t kStageBytes = 8u << 20;
+constexpr int kCopyThreads = 4;
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+void parallel_memcpy(unsigned char* dst, const unsigned char* src, size_t bytes) {
+    if (bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes + kCopyThreads - 1) / kCopyThreads + 63) & ~(size_t)63;
+    std::thread th[kCopyThreads - 1];
+    int nth = 0;
+    for (int k = 1; k < kCopyThreads; ++k) {
+        const size_t lo = (size_t)k * per;
+        if (lo >= bytes) break;
+        th[nth++] = std::thread([=] { memcpy(dst + lo, src + lo, std::min(per, bytes - lo)); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (int k = 0; k < nth; ++k) th[k].join();
+}
+
+// Pinned (or registered) memory is DMA'd in place.  Pageable memory is copied by kCopyThreads threads into a pinned
+// staging ring and DMA'd from there, the copy of piece i+1 overlapping the DMA of piece i.
+int h2d_piece(dte_engine* e, Dev& d, unsigned char* dst, const unsigned char* src, size_t bytes, bool pageable) {
+    if (!pageable || bytes < (256u << 10)) {
+        CUDA_TRY(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.s_h2d));
+        return DTE_OK;
+    }
+    if (!d.h_stage[0]) {
+        for (int b = 0; b < 3; ++b) {
+            CUDA_TRY(e, cudaHostAlloc(reinterpret_cast<void**>(&d.h_stage[b]), kStageBytes, cudaHostAllocDefault));
+            CUDA_TRY(e, cudaEventCreateWithFlags(&d.ev_stage[b], cudaEventDisableTiming));
+        }
+    }
+    for (size_t off = 0; off < bytes; off += kStageBytes) {
+        const size_t len = std::min(kStageBytes, bytes - off);
+        const int b = d.stage_next;
+        d.stage_next = (b + 1) % 3;
+        CUDA_TRY(e, cudaEventSynchronize(d.ev_stage[b]));             // the DMA that last read this staging buffer is done
+        parallel_memcpy(d.h_stage[b], src + off, len);
+        CUDA_TRY(e, cudaMemcpyAsync(dst + off, d.h_stage[b], len, cudaMemcpyHostToDevice, d.s_h2d));
+        CUDA_TRY(e, cudaEventRecord(d.ev_stage[b], d.s_h2d));
+    }
+    return DTE_OK;
+}
+
 void advance_slot(Dev& d) {
     d.cur = (d.cur + 1) % kNumSlots;
     d.slot[d.cur].fill = 0;
@@ -433,11 +482,12 @@ void advance_slot(Dev& d) {
 int land_dev(dte_engine* e, Dev& d, const unsigned char* src, size_t bytes) {
     const size_t cap_bytes = d.cap_tuples * d.g.tuple_bytes();
     CUDA_TRY(e, cudaSetDevice(d.ordinal));
+    const bool pageable = bytes >= (256u << 10) && is_pageable(src);
     while (bytes) {
         Slot& s = d.slot[d.cur];
         if (s.fill == 0) CUDA_TRY(e, cudaStreamWaitEvent(d.s_h2d, s.ev_walk, 0));   // previous walk done with this buffer
         const size_t take = std::min(bytes, cap_bytes - s.fill);
-        CUDA_TRY(e, cudaMemcpyAsync(s.d_tup + s.fill, src, take, cudaMemcpyHostToDevice, d.s_h2d));
+        TRY(h2d_piece(e, d, s.d_tup + s.fill, src, take, pageable));
         s.fill += take;
         src += take;
         bytes -= take;
@@ -546,6 +596,7 @@ int land_group(dte_engine* e, const unsigned char* src, size_t bytes) {
     const size_t cap_bytes = h.cap_tuples * h.g.tuple_bytes();
     static const size_t kMinPiece = 256u << 10;
     uint32_t rot = 0;
+    const bool pageable = bytes >= kMinPiece && is_pageable(src);
     while (bytes) {
         const int b = h.cur;
         const size_t fill = h.slot[b].fill;
@@ -563,7 +614,7 @@ int land_group(dte_engine* e, const unsigned char* src, size_t bytes) {
             Dev& d = e->devs[(pc + rot) % G];
             CUDA_TRY(e, cudaSetDevice(d.ordinal));
             unsigned char* mine = d.slot[b].d_tup + fill + off;
-            CUDA_TRY(e, cudaMemcpyAsync(mine, src + off, len, cudaMemcpyHostToDevice, d.s_h2d));
+            TRY(h2d_piece(e, d, mine, src + off, len, pageable));
             for (Dev& o : e->devs) {
                 if (&o == &d) continue;
                 if (o.ordinal == d.ordinal)
@@ -797,6 +848,10 @@ void destroy_dev(Dev& d) {
     free_ensemble(d);
     free_slots(d);
     if (d.h_ring) cudaFreeHost(d.h_ring);
+    for (int b = 0; b < 3; ++b) {
+        if (d.h_stage[b]) cudaFreeHost(d.h_stage[b]);
+        if (d.ev_stage[b]) cudaEventDestroy(d.ev_stage[b]);
+    }
     for (Slot& s : d.slot) {
         if (s.ev_walk) cudaEventDestroy(s.ev_walk);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
