@@ -85,3 +85,20 @@ def test_sharded_modes(tmp_path, world, mode):
         g, w = got.view(np.float32), want.view(np.float32)
         assert np.allclose(g, w, rtol=1e-5, atol=1e-7)     # north_star tolerance for the one-collective combine
     assert (O.labels(got) == O.labels(want)).mean() > 0.99
+
+
+def test_ensemble_chunk_never_hands_out_an_empty_shard():
+    """(first > 0, count = 0) used to reach dte_load_ensemble on trailing ranks (T < world * ceil(T / world)),
+    which rejects it while the peers wait in a collective.  Now every rank gets the same ValueError up front."""
+    for T, world in [(48, 3), (50, 3), (1024, 8), (8, 8), (9, 8)]:
+        try:
+            chunks = [S.ensemble_chunk(T, r, world) for r in range(world)]
+        except ValueError:
+            assert T == 9                      # ceil(9/8) = 2 trees per chunk would leave ranks 5..7 empty
+            continue
+        assert all(c > 0 for _, c in chunks) and sum(c for _, c in chunks) == T
+        assert [f for f, _ in chunks] == [sum(c for _, c in chunks[:r]) for r in range(world)]
+    for T, world in [(2, 3), (5, 4), (9, 8)]:
+        for r in range(world):                 # the SAME decision on every rank
+            with pytest.raises(ValueError):
+                S.ensemble_chunk(T, r, world)
