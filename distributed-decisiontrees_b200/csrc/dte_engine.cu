@@ -424,7 +424,7 @@ int submit_dev(dte_engine* e, Dev& d, int b) {
 
 // ---- host -> device copy of one piece of the stream ------------------------------------------------------
 constexpr size_t kStageBytes = 8u << 20;
-constexpr int kCopyThreads = 4;
+constexpr int kCopyThreads = 8;
 
 bool is_pageable(const void* p) {
     cudaPointerAttributes a;
