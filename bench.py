@@ -660,6 +660,7 @@ def ensemble_sharded(args, ddt, E, dist, torch, rank, world, local, d_x, d_s, d_
 
     # --- A: ring-order combine, one peer-read kernel ---
     ring_ms = ring_wall = None
+    combine_ms = None
     ring_err = None
     ring_scores = ring_labels = None
     try:
@@ -669,6 +670,18 @@ def ensemble_sharded(args, ddt, E, dist, torch, rank, world, local, d_x, d_s, d_
         if rank == 0:
             ring_scores = out[sel].cpu().numpy().view(np.uint32)
             ring_labels = d_l[sel].cpu().numpy()
+        # the combine kernel alone (the partials are in place, the peers idle at the barrier): its roofline is the NVLink
+        # read of world-1 peer vectors, against the 770 GB/s peer-copy figure of B200_PROFILING.md
+        barrier()
+        if rank == 0:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee.ring_combine_device(rc.ptrs, ne, out, d_l, stream=st)
+            a.record()
+            for _ in range(5):
+                ee.ring_combine_device(rc.ptrs, ne, out, d_l, stream=st)
+            b.record(); torch.cuda.synchronize()
+            combine_ms = a.elapsed_time(b) / 5
+        barrier()
     except Exception as ex:                                        # noqa: BLE001  (IPC not permitted etc.)
         ring_err = str(ex)
         rc = None
@@ -759,6 +772,11 @@ def ensemble_sharded(args, ddt, E, dist, torch, rank, world, local, d_x, d_s, d_
             "ms_per_step": ring_ms if ring_ms else nccl_ms, "tuples_per_s": ne / ((ring_ms if ring_ms else nccl_ms) * 1e-3),
             "combine": "ring-order peer-read kernel (bit-exact)" if ring_ms else "ncclReduce",
             "ring": {"ms_per_step": ring_ms, "wall_ms_per_step": ring_wall, "error": ring_err,
+                     "combine_kernel": None if not combine_ms else {
+                         "ms": combine_ms, "nvlink_bytes": int((world - 1) * 4 * ne), "nvlink_gbs": (world - 1) * 4 * ne / (combine_ms * 1e-3) / 1e9,
+                         "roofline": {"bound": "nvlink", "peak": 770.0, "unit": "GB/s", "frac": (world - 1) * 4 * ne / (combine_ms * 1e-3) / 1e9 / 770.0,
+                                      "peak_source": "measured peer copy per direction per GPU, B200_PROFILING.md"},
+                         "what": "ring_combine_kernel on rank 0: reads %d peer vectors of fp32[%d] over NVLink, adds them in ring order, writes scores + labels" % (world - 1, ne)},
                      "what": "walk -> host barrier -> ONE ring_combine_kernel on rank 0 reading %d peer buffers over NVLink (CUDA IPC) + labels -> host barrier" % (world - 1)},
             "nccl": {"ms_per_step": nccl_ms, "what": "walk -> ONE ncclReduce(SUM) of fp32[%d] to rank 0 -> labels" % ne},
             "ring_vs_nccl_ms": (ring_ms / nccl_ms) if ring_ms else None,

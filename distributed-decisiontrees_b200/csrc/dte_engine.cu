@@ -1554,8 +1554,9 @@ int dte_autotune(dte_t* e, size_t n_tuples, char* report, size_t report_len) {
     CUDA_TRY(e, cudaMalloc(&d_x, n_tuples * F * 4));
     if (cudaMalloc(&d_s, n_tuples * 4) != cudaSuccess) { cudaFree(d_x); return fail(e, DTE_ERR_NOMEM, "autotune: out of device memory"); }
     synth_tuples_kernel<<<(unsigned)d.sm_count * 8, 256, 0, d.s_main>>>(static_cast<uint32_t*>(d_x), 0, (unsigned long long)n_tuples * F, 0x7091E5ull, 10000u, d.g.missing);
-    struct Cand { int ilp, pair, stages, phased; };
-    const Cand cands[] = {{4, 2, 1, 1}, {4, 2, 1, 0}, {2, 4, 1, 1}, {2, 4, 1, 0}, {8, 1, 1, 0}, {8, 1, 2, 0}, {4, 1, 2, 0}, {2, 2, 2, 0}, {2, 2, 1, 0}};
+    struct Cand { int ilp, pair, stages, phased, warps; };      // warps = 10: the 384-thread (168-register) instantiation
+    const Cand cands[] = {{4, 2, 1, 1, 0}, {4, 2, 1, 0, 0}, {4, 2, 1, 1, 10}, {4, 2, 1, 0, 10}, {2, 4, 1, 1, 0}, {2, 4, 1, 0, 0}, {8, 1, 1, 0, 0},
+                          {8, 1, 2, 0, 0}, {4, 1, 2, 0, 0}, {2, 2, 2, 0, 0}, {2, 2, 1, 0, 0}};
     const Tune saved = e->tune;
     Tune best = saved;
     float best_ms = 1e30f;
@@ -1564,9 +1565,13 @@ int dte_autotune(dte_t* e, size_t n_tuples, char* report, size_t report_len) {
     int rc = DTE_OK;
     for (const Cand& c : cands) {
         Tune t = saved;
-        t.ilp = c.ilp; t.pair = c.pair; t.stages = c.stages; t.phased = c.phased;
+        t.ilp = c.ilp; t.pair = c.pair; t.stages = c.stages; t.phased = c.phased; t.warps = c.warps;
         const Plan pl = make_plan(d, t, KERNEL_AUTO);
         if (pl.variant != KERNEL_TILE_STAGED || pl.ilp != c.ilp || pl.pair != c.pair || pl.nstages != c.stages) continue;   // does not fit
+        if (c.warps) {                               // only meaningful when the cap actually removes a tuple group
+            Tune u = t; u.warps = 0;
+            if (make_plan(d, u, KERNEL_AUTO).nwarps <= c.warps) continue;
+        }
         if (c.phased && phased_level(d, t, pl) == 0xFFFFFFFFu) continue;
         float ms = 0;
         for (int rep_i = 0; rep_i < 2 && !rc; ++rep_i) {                     // the second launch is the measurement
