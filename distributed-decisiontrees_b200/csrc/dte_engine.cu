@@ -423,8 +423,8 @@ int submit_dev(dte_engine* e, Dev& d, int b) {
 }
 
 // ---- host -> device copy of one piece of the stream ------------------------------------------------------
-constexpr size_t kStageBytes = 8u << 20;
-constexpr int kCopyThreads = 8;
+constexpr size_t kStageBytes = 16u << 20;
+constexpr int kCopyThreads = 4;
 
 bool is_pageable(const void* p) {
     cudaPointerAttributes a;
