@@ -431,11 +431,9 @@ def main():
             for lo in range(0, tuple_lines.shape[0], write_lines):
                 es.stream_write(tuple_lines[lo:lo + write_lines])
             while got < n_s // 4:
-                lines, flg = es.stream_read_packets(n_s // 4 - got)
-                out_lines[got:got + lines.shape[0]] = lines
-                last[got:got + lines.shape[0]] = flg
-                got += lines.shape[0]
-                if lines.shape[0] == 0:
+                k = es.stream_read_into(out_lines, last, got)       # result lines land in the caller's buffer, no extra copy
+                got += k
+                if k == 0:
                     break
             return time.perf_counter() - t0, got
 

@@ -239,6 +239,16 @@ class Engine:
         self._check(self._lib.dte_ring_combine_device(self._h, arr, len(d_parts), int(n), _ptr(d_out), _ptr(d_labels),
                                                       _stream(stream)))
 
+    def stream_read_into(self, out_lines, last_flags=None, offset=0):
+        """Zero-copy variant: result lines go straight into out_lines[offset:] ([n, 4] fp32, C-contiguous) and the packet
+        flags into last_flags[offset:] (u8); returns the number of lines read."""
+        room = out_lines.shape[0] - int(offset)
+        got = C.c_size_t()
+        po = C.c_void_p(out_lines.ctypes.data + 16 * int(offset))
+        pl = C.c_void_p(last_flags.ctypes.data + int(offset)) if last_flags is not None else None
+        self._check(self._lib.dte_stream_read_packets(self._h, po, pl, room, C.byref(got)))
+        return int(got.value)
+
     def process_done(self):
         d = C.c_int()
         self._check(self._lib.dte_process_done(self._h, C.byref(d)))
