@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "dte_engine.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "dte_kernels.cuh"), os.path.join(HERE, "csrc", "dte_device.cuh"),
-        os.path.join(HERE, "..", "include", "dte.h")]
+        os.path.join(HERE, "..", "include", "dte.h"), os.path.join(HERE, "csrc", "dte_partition.hpp")]
 OUT = os.path.join(HERE, "libdte.so")
 
 NVCC_FLAGS = [
@@ -106,3 +106,19 @@ def build_pack_check(force=False):
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     return PACK_OUT
+
+
+PART_SRC = os.path.join(HERE, "..", "tools", "partition_check.cpp")
+PART_OUT = os.path.join(HERE, "..", "tools", "partition_check")
+
+
+def build_partition_check(force=False):
+    """Brute-force check of csrc/dte_partition.hpp (the data-sharded index arithmetic); CPU test tier."""
+    deps = [PART_SRC, os.path.join(HERE, "csrc", "dte_partition.hpp")]
+    if not force and os.path.exists(PART_OUT) and all(os.path.getmtime(PART_OUT) >= os.path.getmtime(d) for d in deps):
+        return PART_OUT
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    res = subprocess.run([gxx, "-O2", "-std=c++17", "-o", PART_OUT, PART_SRC], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return PART_OUT

@@ -12,6 +12,7 @@
 //   completion / counters .... rtl/DTEngine/DTInference.sv:314-374,633-663
 #include "../../include/dte.h"
 #include "dte_device.cuh"
+#include "dte_partition.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -477,8 +478,8 @@ void advance_slot(Dev& d) {
     d.slot[d.cur].walked = 0;
 }
 
-// Land `bytes` of the tuple stream on device d (H2D straight from the caller's buffer — pinned memory is DMA'd
-// in place, pageable memory goes through the driver's staging).  Full slots are submitted as they fill.
+// Land `bytes` of the tuple stream on device d (pinned memory is DMA'd in place, pageable memory goes through the
+// engine's staging ring, h2d_piece).  Full slots are submitted as they fill.
 int land_dev(dte_engine* e, Dev& d, const unsigned char* src, size_t bytes) {
     const size_t cap_bytes = d.cap_tuples * d.g.tuple_bytes();
     CUDA_TRY(e, cudaSetDevice(d.ordinal));
@@ -679,29 +680,26 @@ void reset_pipeline(Dev& d) {
     d.tuples_landed = 0;
 }
 
-// Results exposed by this handle, in order: tuple i lives on device dev at local index loc.
+// Results exposed by this handle, in order: tuple i lives on device dev at local index loc (dte_partition.hpp).
 void locate_result(const dte_engine* e, uint64_t i, int& dev, uint64_t& loc) {
     if (e->multi() && e->deal) {
-        const uint64_t bt = e->deal_lines / e->g.tuple_cls, G = e->devs.size();
-        const uint64_t q = i / bt;
-        dev = e->pos2dev[q % G];
-        loc = (q / G) * bt + i % bt;
+        const Deal deal{e->deal_lines / e->g.tuple_cls, e->devs.size()};
+        uint64_t pos;
+        deal.locate(i, pos, loc);
+        dev = e->pos2dev[pos];
     } else {
         dev = e->group ? e->pos2dev[0] : 0;
         loc = i;
     }
 }
-// how many leading results (in exposed order) a per-device local count stands for
+// how many leading results (in exposed order) the per-device local counts stand for
 uint64_t global_prefix(const dte_engine* e, bool completed) {
     auto cnt = [&](const Dev& d) { return completed ? d.res_done : d.res_enq; };
     if (e->multi() && e->deal) {
-        const uint64_t bt = e->deal_lines / e->g.tuple_cls, G = e->devs.size();
-        uint64_t best = ~0ull;
-        for (uint64_t r = 0; r < G; ++r) {           // first missing tuple of ring position r, as a global index
-            const uint64_t c = cnt(e->devs[(size_t)e->pos2dev[r]]);
-            best = std::min(best, (c / bt * G + r) * bt + c % bt);
-        }
-        return best;
+        const Deal deal{e->deal_lines / e->g.tuple_cls, e->devs.size()};
+        uint64_t c[kMaxRing];
+        for (size_t r = 0; r < e->devs.size(); ++r) c[r] = cnt(e->devs[(size_t)e->pos2dev[r]]);
+        return deal.prefix(c);
     }
     return cnt(e->devs[(size_t)(e->group ? e->pos2dev[0] : 0)]);
 }
@@ -740,7 +738,6 @@ int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_
     if (e->state == dte_engine::ST_TREES) return fail(e, DTE_ERR_STATE, "infer_host while the tree stream is being received");
     if (fragment_pending(e)) return fail(e, DTE_ERR_STATE, "a partial tuple is pending in the line stream");
     TRY(drain_all(e));
-    const bool saved_group = e->group, saved_deal = e->deal;
     if (e->multi()) TRY(decide_partition(e, g));
     TRY(check_resident(e, g));
     if (n == 0) return DTE_OK;
@@ -812,7 +809,6 @@ int infer_host(dte_engine* e, const unsigned char* h_tuples, size_t n, float* h_
         d.res_enq = d.res_done = enq0[i];            // direct-sink results are not part of the line-stream queue
     }
     e->last_walk_ms = ms_max;
-    if (!e->multi()) { e->group = saved_group; e->deal = saved_deal; }
     if (rc || rc2) return rc ? rc : rc2;
     e->tuples_in += n;
     return DTE_OK;

@@ -120,3 +120,12 @@ def test_repacker_on_the_cpu_against_the_oracle(tmp_path):
                 xi = np.ascontiguousarray(x[i])
                 want = lib.dteo_leaf(C.byref(cfg), wt.ctypes.data, ft.ctypes.data, xi.ctypes.data)
                 assert got[i, t] == want, (D, t, i)
+
+
+def test_partition_arithmetic_against_a_brute_force_deal():
+    """csrc/dte_partition.hpp (global tuple -> ring position / local index; covered prefix from per-device counts) against a
+    literal simulation of PCIeReceiver's batch dealing (PCIeReceiver.sv:298-307) over random (batch, devices, tuples)."""
+    import subprocess
+    from ddt_b200 import build as B
+    out = subprocess.run([B.build_partition_check()], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
