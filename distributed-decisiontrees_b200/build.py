@@ -122,3 +122,24 @@ def build_partition_check(force=False):
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
     return PART_OUT
+
+
+def build_evidence_tools(force=False):
+    """tools/racecheck_canonical (the textbook bulk-copy ring run under racecheck) and tools/pipe_microbench (cycles per
+    warp-wide access on the shared-memory / L1 pipe): the small CUDA programs behind profiles/r02_summary.md."""
+    nvcc = nvcc_path()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found")
+    outs = []
+    for name in ("racecheck_canonical", "pipe_microbench"):
+        src = os.path.join(HERE, "..", "tools", name + ".cu")
+        out = os.path.join(HERE, "..", "tools", name)
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            cmd = [nvcc, "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-o", out, src]
+            if os.path.exists("/usr/bin/g++"):
+                cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        outs.append(out)
+    return outs
