@@ -217,6 +217,22 @@ lines_kat = dict(
     expect_lines=[[f(1.0), f(2.0), f(3.0), f(4.0)]],
 )
 
+# data dealing (PCIeReceiver.sv:298-307): currDCount counts the lines of the current batch up to core_data_batch_cls - 1,
+# then currDevID moves to the next entry of devices_list and wraps at numDevs; the host node (entry 0) goes first.
+deal_kat = dict(
+    name="deal_batches_round_robin",
+    why="11 data lines, core_data_batch_cls = 2, numDevs = 3: lines {0,1}->dev0 {2,3}->dev1 {4,5}->dev2 {6,7}->dev0 {8,9}->dev1 {10}->dev2",
+    n_lines=11, batch_cls=2, num_devs=3,
+    expect=[[[0, 2], [6, 2]], [[2, 2], [8, 2]], [[4, 2], [10, 1]]],      # per device: (first line, number of lines)
+)
+# tree chunking (PCIeReceiver.sv:241-264): the weights stream is cut every numcls_local_weights lines, the index stream every
+# numcls_local_findexes lines, chunk i -> devices_list[i % numDevs]; contiguous trees per device, host node first.
+chunk_kat = dict(
+    name="contiguous_tree_chunks",
+    why="7 trees over 3 devices in chunks of ceil(7/3) = 3 trees: dev0 trees 0-2, dev1 trees 3-5, dev2 tree 6",
+    n_trees=7, num_devs=3, expect=[[0, 3], [3, 3], [6, 1]],
+)
+
 # ring combine (ResultsCombiner.sv:292-311,359-368): ((p_host + p_1) + p_2)
 ring = dict(
     name="ring_order_3dev",
@@ -225,7 +241,8 @@ ring = dict(
     expect=[0, f(6.0)],
 )
 
-out = {"about": "hand-derived KATs; see make_kats.py for the derivations", "cases": cases, "ring": [ring], "lines": [lines_kat]}
+out = {"about": "hand-derived KATs; see make_kats.py for the derivations", "cases": cases, "ring": [ring], "lines": [lines_kat], "deal": [deal_kat],
+       "chunks": [chunk_kat]}
 with open(os.path.join(HERE, "kats.json"), "w") as fh:
     json.dump(out, fh, indent=1)
 print("wrote", len(cases), "cases")

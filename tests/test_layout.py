@@ -129,3 +129,15 @@ def test_partition_arithmetic_against_a_brute_force_deal():
     from ddt_b200 import build as B
     out = subprocess.run([B.build_partition_check()], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_dealing_and_chunking_kats(kats):
+    """Hand-derived vectors for the two partition rules of PCIeReceiver (batch dealing :298-307, tree chunks :241-264)
+    against the host-side helpers the multi-process path uses."""
+    import ddt_b200 as ddt
+    for k in kats["deal"]:
+        got = ddt.sharding.deal_batches(k["n_lines"], k["batch_cls"], k["num_devs"])
+        assert [[list(x) for x in dev] for dev in got] == k["expect"], k["name"]
+    for k in kats["chunks"]:
+        got = [list(ddt.sharding.ensemble_chunk(k["n_trees"], r, k["num_devs"])) for r in range(k["num_devs"])]
+        assert got == k["expect"], k["name"]
