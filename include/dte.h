@@ -66,10 +66,19 @@ const char* dte_last_error(const dte_t* engine);
 
 /* ---- soft registers ------------------------------------------------------------------------ */
 /* Replaces the SoftRegReq/SoftRegResp bus, addresses >= 200 (rtl/ManagerSoftRegs.sv:63):
- * writes 200..211 as decoded in rtl/DTEngine/EngineCSR.sv:189-306, reads 220..226 as in
- * EngineCSR.sv:113-125 (222/223 = progCycles/execCycles, here in nanoseconds of device time),
- * 121..126 = appStatus counters (rtl/ManagerSoftRegs.sv:122-127); any other read address returns
- * 0xFFFFFFFFFFFFFFFF like EngineCSR.sv:123. Writing bit 0 of register 200 is `start`. */
+ * writes 200..211 as decoded in rtl/DTEngine/EngineCSR.sv:189-306; writing bit 0 of register 200 is `start`.
+ * Reads (any other address returns 0xFFFFFFFFFFFFFFFF like EngineCSR.sv:123):
+ *   220 receiver FSM state (0 idle, 1 trees, 3 data; idle again after process_done, PCIeReceiver.sv:289-292)
+ *   221 lines received since start
+ *   222 progCycles  = first tree line -> ensemble resident     } rtl/DTEngine/DTInference.sv:330-357; host clock, in
+ *   223 execCycles  = start -> process_done (running: -> now)   } nanoseconds, or cycles of an f-MHz clock (DTE_OPT_CYCLE_MHZ)
+ *   224..226 lines / packets that left for other ring positions (num_sent_lines, num_sent_packets, packets_lines)
+ *   121..126 appStatus[0..5] in the reference's packing, PAIRS of 32-bit counters (DTInference.sv:367-372):
+ *       {cluster_out_valids, cluster_tuples_res_out[0]} {num_out_tuples, cluster_tree_res_out[0]} {data_lines, prog_lines}
+ *       {aggreg_tuples_in, cluster_reduce_tree_outs[0]} {cluster_reduce_tree_outs_valids[0], sl3_res_lines}
+ *       {cluster_tuples_received[0], cluster_lines_received[0]}
+ *     modelled from the run's counts: tuple i is served by clusters (i*K)%8 .. +K-1 (Core.sv:305-316); Core counters
+ *     restart at `start`, the cluster counters only at create (DTPUCluster.sv:85-97). */
 int dte_softreg_write(dte_t* engine, uint32_t addr, uint64_t data);
 int dte_softreg_read(dte_t* engine, uint32_t addr, uint64_t* data);
 
@@ -80,7 +89,8 @@ int dte_softreg_read(dte_t* engine, uint32_t addr, uint64_t* data);
  * 201[63:32]) round-robin unless broadcast_data (rtl/DTEngine/PCIeReceiver.sv:160-178,241-264,
  * 298-307).  One process per GPU replays the SAME stream into its engine; engine g keeps what the
  * ring would have delivered to device g.  Results: aggregate mode -> partial scores (combine with
- * one NCCL reduce / dte_ring_add_device); otherwise -> the scores of the local tuples, local order. */
+ * dte_ring_combine_device over CUDA-IPC buffers, or one NCCL reduce); otherwise -> the scores of the local tuples,
+ * local order.  Single-device handles only (a handle from dte_create_multi owns every ring position). */
 int dte_set_node(dte_t* engine, uint32_t node_index);
 
 /* ---- PCIe line streams --------------------------------------------------------------------- */
